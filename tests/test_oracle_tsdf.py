@@ -1,0 +1,79 @@
+"""Pin the C restatement (oracle/tsdf_oracle.c) to the reference.
+
+Two anchors:
+  * tests/golden/tsdf_golden.npz -- digests of world.pcd written by the VERBATIM reference binary
+    (oracle/_ref/Integrate_ref, built from the untouched /root/reference sources);
+  * where that binary is present (build container, and the GPU box, where it travels as a built file)
+    it is re-run live on freshly generated inputs and compared record by record.
+Bit-exact in both cases: the restatement follows the reference's float/double evaluation order.
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+import helpers
+from elasticreconstruction_b200 import synth
+
+GOLD = np.load(os.path.join(os.path.dirname(__file__), "golden", "tsdf_golden.npz"))
+STRIDE = 997
+
+
+@pytest.mark.parametrize("mk", helpers.ALL_SCENES, ids=lambda f: f.__name__)
+def test_oracle_matches_golden(oracle, mk):
+    sc = mk()
+    vol = oracle.OracleTSDF()
+    helpers.run_scene(vol, sc, mul=oracle.mat4_mul)
+    world = oracle.sort_world(vol.extract())
+    name = sc["name"]
+    assert len(world) == int(GOLD[name + "_count"])
+    assert np.array_equal(world[::STRIDE].view(np.uint32), GOLD[name + "_sample"].view(np.uint32))
+    assert oracle.world_digest(world) == str(GOLD[name + "_digest"])
+
+
+@pytest.mark.parametrize("mk", [helpers.scene_room, helpers.scene_ctr], ids=lambda f: f.__name__)
+def test_oracle_matches_live_reference(oracle, mk):
+    if not os.path.exists(oracle.REF_INTEGRATE):
+        pytest.skip("oracle/_ref/Integrate_ref not built (needs /root/reference at build time)")
+    sc = mk()
+    with tempfile.TemporaryDirectory() as d:
+        args = helpers.write_scene(sc, d)
+        oracle.run_reference_integrate(args, cwd=d)
+        ref = oracle.sort_world(synth.read_pcd_xyzi(os.path.join(d, "world.pcd")))
+    vol = oracle.OracleTSDF()
+    helpers.run_scene(vol, sc, mul=oracle.mat4_mul)
+    mine = oracle.sort_world(vol.extract())
+    assert mine.shape == ref.shape
+    assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32))
+
+
+def test_inverse_is_an_inverse(oracle):
+    rng = np.random.default_rng(1)
+    for _ in range(50):
+        T = synth.make_pose(synth.rot_axis(rng.normal(size=3), rng.uniform(0, 3)), rng.normal(size=3))
+        Ti = oracle.mat4_inverse(T)
+        assert np.allclose(Ti @ T, np.eye(4), atol=1e-13)
+        assert np.allclose(Ti, np.linalg.inv(T), atol=1e-13)
+
+
+def test_scale_depth_properties(oracle):
+    vol = oracle.OracleTSDF()
+    d = np.zeros((480, 640), dtype=np.uint16)
+    d[100, 200] = 1000
+    d[0, 0] = 2400          # ray length > 2.5 m at the corner -> zeroed (TSDFVolume.cpp:29-33)
+    d[240, 320] = 2500
+    d[240, 321] = 2499
+    s = vol.scale_depth(d)
+    assert s[0, 0] == 0.0 and s[5, 5] == 0.0
+    lam = np.sqrt(np.float32(((200 - 319.5) / 525.0) ** 2 + ((100 - 239.5) / 525.0) ** 2 + 1))
+    assert abs(s[100, 200] - lam) < 1e-6
+    assert s[240, 320] == 0.0        # lambda > 1 even half a pixel off-centre: 2.5000023 > 2.5 -> 0
+    assert 2.499 < s[240, 321] < 2.5
+    assert s.dtype == np.float32
+
+
+def test_empty_frame_touches_nothing(oracle):
+    vol = oracle.OracleTSDF()
+    assert vol.integrate(np.zeros((480, 640), dtype=np.uint16), np.eye(4)) == 0
+    assert vol.num_blocks() == 0 and len(vol.extract()) == 0
