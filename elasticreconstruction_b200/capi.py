@@ -1,0 +1,285 @@
+"""ctypes binding of libelastic_b200.so (the C ABI declared in include/elastic_b200.h).
+
+This is the Python face of the product used by tests/ and bench.py; the drop-in executables under
+apps/ bind the same entry points from C++.  There is no fallback path: if the shared library has not
+been built (python -m elasticreconstruction_b200.build) importing a symbol raises, and creating a
+handle on a machine without a CUDA device raises with the library's error text.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libelastic_b200.so")
+
+_lib = None
+
+c_dp = C.POINTER(C.c_double)
+c_fp = C.POINTER(C.c_float)
+c_u16p = C.POINTER(C.c_uint16)
+c_ip = C.POINTER(C.c_int)
+c_i32p = C.POINTER(C.c_int32)
+c_u64p = C.POINTER(C.c_uint64)
+c_szp = C.POINTER(C.c_size_t)
+
+# name -> (restype, argtypes); kept in one table so tests can check it against include/elastic_b200.h
+SIGNATURES = {
+    "er_last_error": (C.c_char_p, []),
+    "er_version": (C.c_int, []),
+    "er_build_arch": (C.c_char_p, []),
+    "er_mat4_mul": (None, [c_dp, c_dp, c_dp]),
+    "er_mat4_inverse": (None, [c_dp, c_dp]),
+    "er_tsdf_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_size_t]),
+    "er_tsdf_destroy": (None, [C.c_void_p]),
+    "er_tsdf_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "er_tsdf_set_camera": (C.c_int, [C.c_void_p] + [C.c_float] * 5),
+    "er_tsdf_set_control_grids": (C.c_int, [C.c_void_p, c_fp, C.c_int, C.c_int, C.c_float]),
+    "er_tsdf_set_partition": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
+    "er_tsdf_set_stats": (C.c_int, [C.c_void_p, C.c_int]),
+    "er_tsdf_get_stats": (C.c_int, [C.c_void_p, c_u64p, c_u64p, c_u64p]),
+    "er_tsdf_reproject": (C.c_int, [C.c_void_p, c_u16p, c_dp, c_dp, c_dp, c_dp, C.c_int]),
+    "er_tsdf_integrate": (C.c_int, [C.c_void_p, c_u16p, c_dp]),
+    "er_tsdf_integrate_ctr": (C.c_int, [C.c_void_p, c_u16p, c_dp, c_dp, c_dp, c_dp, C.c_int]),
+    "er_tsdf_integrate_batch": (C.c_int, [C.c_void_p, c_u16p, c_dp, C.c_int]),
+    "er_tsdf_integrate_device": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, C.c_int]),
+    "er_tsdf_profile_device": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, C.c_int, c_fp, c_fp]),
+    "er_tsdf_set_fusion": (C.c_int, [C.c_void_p, C.c_int]),
+    "er_tsdf_sync": (C.c_int, [C.c_void_p]),
+    "er_tsdf_num_blocks": (C.c_int, [C.c_void_p, c_ip]),
+    "er_tsdf_block_keys": (C.c_int, [C.c_void_p, c_ip, C.c_int]),
+    "er_tsdf_read_block": (C.c_int, [C.c_void_p, C.c_int, c_fp, c_fp]),
+    "er_tsdf_extract": (C.c_int, [C.c_void_p, c_fp, C.c_size_t, c_szp]),
+    "er_tsdf_event_record": (C.c_int, [C.c_void_p, C.c_int]),
+    "er_tsdf_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_fp]),
+    "er_tsdf_launch_count": (C.c_uint64, [C.c_void_p]),
+    "er_cloud_upload": (C.c_void_p, [C.c_int, c_fp, c_fp, C.c_size_t, C.c_double]),
+    "er_cloud_free": (None, [C.c_void_p]),
+    "er_cloud_size": (C.c_size_t, [C.c_void_p]),
+    "er_icp_count_inliers": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, C.c_double, c_ip]),
+    "er_icp_align": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, C.c_double, C.c_int, C.c_double, C.c_int, c_dp, c_ip, c_dp]),
+    "er_icp_align_batch": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, c_ip, c_ip, C.c_int, c_dp, C.c_double, C.c_int,
+                                     C.c_double, C.c_int, c_dp, c_ip, c_dp]),
+    "er_icp_correspondences": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, C.c_double, C.c_double, c_i32p, C.c_size_t,
+                                         c_szp, c_dp]),
+    "er_icp_event_record": (C.c_int, [C.c_int, C.c_int]),
+    "er_icp_event_elapsed_ms": (C.c_int, [C.c_int, C.c_int, C.c_int, c_fp]),
+    "er_icp_launch_count": (C.c_uint64, [C.c_int]),
+    "er_icp_sync": (C.c_int, [C.c_int]),
+}
+
+
+class ElasticError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libelastic_b200.so; raises if it has not been built -- there is no CPU fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ElasticError(LIB_PATH + " is missing: run `python -m elasticreconstruction_b200.build` "
+                               "(the CUDA extension is the product; there is no fallback path)")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)      # AttributeError if the library lacks a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise ElasticError("libelastic_b200: rc=%d: %s" % (rc, lib().er_last_error().decode("utf-8", "replace")))
+
+
+def _dp(a):
+    return a.ctypes.data_as(c_dp)
+
+
+def _fp(a):
+    return a.ctypes.data_as(c_fp)
+
+
+def _u16p(a):
+    return a.ctypes.data_as(c_u16p)
+
+
+def _mat(T):
+    return np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+
+
+def mat4_mul(a, b) -> np.ndarray:
+    out = np.empty(16, dtype=np.float64)
+    lib().er_mat4_mul(_dp(_mat(a)), _dp(_mat(b)), _dp(out))
+    return out.reshape(4, 4)
+
+
+def mat4_inverse(m) -> np.ndarray:
+    out = np.empty(16, dtype=np.float64)
+    lib().er_mat4_inverse(_dp(_mat(m)), _dp(out))
+    return out.reshape(4, 4)
+
+
+class TSDFVolume:
+    """Device-resident counterpart of the reference's TSDFVolume (Integrate/TSDFVolume.h:14-69)."""
+
+    def __init__(self, cols: int = 640, rows: int = 480, device: int = 0, max_blocks: int = 1024,
+                 voxel: float = 0.0, trunc: float = 0.0):
+        self.cols, self.rows = cols, rows
+        h = lib().er_tsdf_create(device, cols, rows, voxel, 64, trunc, max_blocks)
+        if not h:
+            raise ElasticError("er_tsdf_create failed: " + lib().er_last_error().decode("utf-8", "replace"))
+        self._h = C.c_void_p(h)
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().er_tsdf_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- configuration
+    def set_stream(self, cuda_stream_ptr: int):
+        _check(lib().er_tsdf_set_stream(self._h, C.c_void_p(cuda_stream_ptr)))
+
+    def set_camera(self, fx, fy, cx, cy, integration_trunc):
+        _check(lib().er_tsdf_set_camera(self._h, fx, fy, cx, cy, integration_trunc))
+
+    def set_control_grids(self, grids, res: int, length: float):
+        g = np.ascontiguousarray(grids, dtype=np.float32)
+        num = g.shape[0]
+        assert g.size == num * (res + 1) ** 3 * 3
+        _check(lib().er_tsdf_set_control_grids(self._h, _fp(g), num, res, length))
+        self._grids_key = (id(grids), res, length)
+
+    def set_partition(self, rank: int, world: int):
+        _check(lib().er_tsdf_set_partition(self._h, rank, world))
+
+    def set_stats(self, enable: bool):
+        _check(lib().er_tsdf_set_stats(self._h, int(enable)))
+
+    def set_fusion(self, frames_per_launch: int):
+        _check(lib().er_tsdf_set_fusion(self._h, frames_per_launch))
+
+    def stats(self):
+        a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(lib().er_tsdf_get_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
+        return dict(frames=a.value, touched_blocks=b.value, updated_voxels=c.value)
+
+    # -- the hot path
+    def integrate(self, depth, T):
+        """ScaleDepth + Integrate (IntegrateApp.cpp:224-225) for one host frame; asynchronous."""
+        d = np.ascontiguousarray(depth, dtype=np.uint16)
+        assert d.size == self.cols * self.rows
+        _check(lib().er_tsdf_integrate(self._h, _u16p(d), _dp(_mat(T))))
+
+    def integrate_batch(self, depth, T):
+        d = np.ascontiguousarray(depth, dtype=np.uint16)
+        Ts = np.ascontiguousarray(T, dtype=np.float64).reshape(-1, 16)
+        n = Ts.shape[0]
+        assert d.size == n * self.cols * self.rows
+        _check(lib().er_tsdf_integrate_batch(self._h, _u16p(d), _dp(Ts), n))
+
+    def integrate_ptr(self, host_ptr: int, T, n: int):
+        """Frames in (pinned) host memory given by raw address (e.g. a torch pinned tensor's data_ptr)."""
+        Ts = np.ascontiguousarray(T, dtype=np.float64).reshape(-1, 16)
+        _check(lib().er_tsdf_integrate_batch(self._h, C.cast(C.c_void_p(host_ptr), c_u16p), _dp(Ts), n))
+
+    def integrate_device(self, device_ptr: int, T, n: int):
+        """Frames already resident in HBM (device pointer)."""
+        Ts = np.ascontiguousarray(T, dtype=np.float64).reshape(-1, 16)
+        assert Ts.shape[0] >= n
+        _check(lib().er_tsdf_integrate_device(self._h, C.c_void_p(device_ptr), _dp(Ts), n))
+
+    def profile_device(self, device_ptr: int, T, n: int):
+        """Per-kernel device time over n resident frames: (touch_ms, integrate_ms), event-bracketed."""
+        Ts = np.ascontiguousarray(T, dtype=np.float64).reshape(-1, 16)
+        a, b = C.c_float(), C.c_float()
+        _check(lib().er_tsdf_profile_device(self._h, C.c_void_p(device_ptr), _dp(Ts), n, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def reproject(self, depth, Ti, T0, A0, Ai, grid_or_chunk, res=None, length=None):
+        """CIntegrateApp::Reproject on one frame; returns the new depth image.
+
+        `grid_or_chunk` is either the chunk index into the grids given to set_control_grids(), or (for
+        signature compatibility with the oracle) one lattice array, which is then uploaded as chunk 0."""
+        d = np.array(depth, dtype=np.uint16, order="C", copy=True)
+        chunk = grid_or_chunk
+        if not isinstance(grid_or_chunk, (int, np.integer)):
+            g = np.ascontiguousarray(grid_or_chunk, dtype=np.float32)
+            self.set_control_grids(g.reshape(1, -1, 3), res, length)
+            chunk = 0
+        _check(lib().er_tsdf_reproject(self._h, _u16p(d), _dp(_mat(Ti)), _dp(_mat(T0)), _dp(_mat(A0)),
+                                       _dp(_mat(Ai)), int(chunk)))
+        return d
+
+    def integrate_ctr(self, depth, Ti, T0, A0, Ai, chunk: int):
+        d = np.ascontiguousarray(depth, dtype=np.uint16)
+        _check(lib().er_tsdf_integrate_ctr(self._h, _u16p(d), _dp(_mat(Ti)), _dp(_mat(T0)), _dp(_mat(A0)),
+                                           _dp(_mat(Ai)), int(chunk)))
+
+    def sync(self):
+        _check(lib().er_tsdf_sync(self._h))
+
+    # -- inspection / output
+    def num_blocks(self) -> int:
+        n = C.c_int()
+        _check(lib().er_tsdf_num_blocks(self._h, C.byref(n)))
+        return n.value
+
+    def block_keys(self) -> np.ndarray:
+        n = self.num_blocks()
+        keys = np.empty(n, dtype=np.int32)
+        if n:
+            _check(lib().er_tsdf_block_keys(self._h, keys.ctypes.data_as(c_ip), n))
+        return keys
+
+    def read_block(self, key: int):
+        sdf = np.empty(64 ** 3, dtype=np.float32)
+        w = np.empty(64 ** 3, dtype=np.float32)
+        _check(lib().er_tsdf_read_block(self._h, int(key), _fp(sdf), _fp(w)))
+        return sdf, w
+
+    def extract(self) -> np.ndarray:
+        """SaveWorld predicate (TSDFVolume.cpp:104-132): float32 [n,4] = x,y,z (voxel units), tsdf."""
+        n = C.c_size_t()
+        _check(lib().er_tsdf_extract(self._h, None, 0, C.byref(n)))
+        out = np.empty((n.value, 4), dtype=np.float32)
+        if n.value:
+            m = C.c_size_t()
+            _check(lib().er_tsdf_extract(self._h, _fp(out), n.value, C.byref(m)))
+            assert m.value == n.value
+        return out
+
+    def save_world(self, path: str) -> int:
+        """Write world.pcd exactly as pcl::io::savePCDFile(binary) does for PointXYZI (TSDFVolume.cpp:130)."""
+        pts = self.extract()
+        n = len(pts)
+        hdr = ("# .PCD v0.7 - Point Cloud Data file format\nVERSION 0.7\nFIELDS x y z intensity\n"
+               "SIZE 4 4 4 4\nTYPE F F F F\nCOUNT 1 1 1 1\nWIDTH %d\nHEIGHT 1\n"
+               "VIEWPOINT 0 0 0 1 0 0 0\nPOINTS %d\nDATA binary\n" % (n, n))
+        with open(path, "wb") as f:
+            f.write(hdr.encode("ascii"))
+            f.write(pts.astype("<f4").tobytes())
+        return n
+
+    # -- device timing
+    def event_record(self, slot: int):
+        _check(lib().er_tsdf_event_record(self._h, slot))
+
+    def event_elapsed_ms(self, a: int, b: int) -> float:
+        ms = C.c_float()
+        _check(lib().er_tsdf_event_elapsed_ms(self._h, a, b, C.byref(ms)))
+        return ms.value
+
+    def launch_count(self) -> int:
+        return int(lib().er_tsdf_launch_count(self._h))

@@ -1,0 +1,160 @@
+/*
+ * elastic_b200.h -- C ABI of libelastic_b200.so, the B200-native (sm_100a) replacement for the two
+ * data-parallel hot paths of qianyizh/ElasticReconstruction:
+ *
+ *   TSDF integration   Integrate/TSDFVolume.{h,cpp}, TSDFVolumeUnit.{h,cpp}, ControlGrid.{h,cpp},
+ *                      IntegrateApp.cpp:190-269
+ *   pairwise ICP       BuildCorrespondence/CorresApp.cpp:112-319 (+ the PCL 1.7 calls it makes)
+ *
+ * The reference has no plugin/FFI surface: its boundary is two executables.  The entry
+ * points below are cut at the granularity of the reference's own methods so that each has an oracle
+ * counterpart; the drop-in executables (apps/Integrate, apps/BuildCorrespondence) are thin C++ hosts
+ * over exactly these calls.  Each declaration cites the reference code it replaces (paths relative to
+ * the reference checkout).
+ *
+ * Conventions
+ *   - every function returns 0 on success, <0 on error; er_last_error() returns the message of the
+ *     last failure on the calling thread.  No exception crosses the ABI.
+ *   - plain pointers and sizes only; the caller owns every host buffer.  Pointers named d_* are CUDA
+ *     device pointers on the handle's device, everything else is host memory.
+ *   - matrices are row-major double[16], camera->world like the reference's .log files
+ *     (Integrate/TSDFVolume.cpp:49).
+ *   - a handle is bound to one CUDA device and one stream and is not thread-safe; distinct handles are.
+ *   - there is no CPU fallback: creating a handle without a usable CUDA device fails.
+ */
+#ifndef ELASTIC_B200_H_
+#define ELASTIC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ER_OK 0
+#define ER_ERR_CUDA (-1)
+#define ER_ERR_ARG (-2)
+#define ER_ERR_CAPACITY (-3)
+
+const char* er_last_error(void);
+/* Library/ABI version and the CUDA arch the kernels were built for ("sm_100a"). */
+int er_version(void);
+const char* er_build_arch(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * Host-side 4x4 helpers with the reference's (Eigen 3.1.2) evaluation order, exported because the
+ * hosts compose trajectories with them:  traj[i*I+j] = pose[i] * seg[i*I+j]  (IntegrateApp.cpp:73).
+ * ---------------------------------------------------------------------------------------------- */
+void er_mat4_mul(const double a[16], const double b[16], double out[16]);
+void er_mat4_inverse(const double m[16], double out[16]);      /* Matrix4d::inverse(), TSDFVolume.cpp:40 */
+
+/* ================================================================================================
+ * TSDF volume  (class TSDFVolume, Integrate/TSDFVolume.h:14-69)
+ * ============================================================================================== */
+typedef struct er_tsdf er_tsdf;
+
+/* TSDFVolume::TSDFVolume (TSDFVolume.cpp:6-13).  voxel/trunc <= 0 select the reference constants
+ * 3.0/512 m and 0.03 m; block_res must be 64 (TSDFVolume.cpp:57); max_blocks sizes the device pool of
+ * 64^3 (sdf,weight) float2 blocks (2 MiB each; 0 = 1024). */
+er_tsdf* er_tsdf_create(int device, int cols, int rows, double voxel, int block_res, double trunc, size_t max_blocks);
+void er_tsdf_destroy(er_tsdf* v);
+
+/* Use an existing CUDA stream (cudaStream_t cast to void*) for all work of this handle. */
+int er_tsdf_set_stream(er_tsdf* v, void* cuda_stream);
+/* CameraParam (TSDFVolumeUnit.h:65-96): fx fy cx cy integration_trunc. */
+int er_tsdf_set_camera(er_tsdf* v, float fx, float fy, float cx, float cy, float integration_trunc);
+/* ControlGrid::Load for `num` fragments (ControlGrid.cpp:15-34): ctr_xyz = num*(res+1)^3*3 floats. */
+int er_tsdf_set_control_grids(er_tsdf* v, const float* ctr_xyz, int num, int res, float length);
+/* Multi-GPU block partition: this handle integrates only blocks with (xi+yi+zi) % world == rank. */
+int er_tsdf_set_partition(er_tsdf* v, int rank, int world);
+/* Count updated voxels / touched blocks in the kernels (roofline bookkeeping; small cost). */
+int er_tsdf_set_stats(er_tsdf* v, int enable);
+int er_tsdf_get_stats(er_tsdf* v, uint64_t* frames, uint64_t* touched_blocks, uint64_t* updated_voxels);
+
+/* CIntegrateApp::Reproject (IntegrateApp.cpp:228-269) on one frame: depth is rewritten in place.
+ * Ti = traj[frame-1], T0 = traj[0], A0 = seg_traj[0], Ai = seg_traj[frame-1], chunk = (frame-1)/interval. */
+int er_tsdf_reproject(er_tsdf* v, uint16_t* depth_inout, const double Ti[16], const double T0[16],
+                      const double A0[16], const double Ai[16], int chunk);
+
+/* TSDFVolume::ScaleDepth + TSDFVolume::Integrate, the pair of calls at IntegrateApp.cpp:224-225.
+ * Asynchronous: returns once the frame is staged and the kernels are enqueued. */
+int er_tsdf_integrate(er_tsdf* v, const uint16_t* depth, const double T[16]);
+/* Reproject + ScaleDepth + Integrate without the host round trip (IntegrateApp.cpp:217-225). */
+int er_tsdf_integrate_ctr(er_tsdf* v, const uint16_t* depth, const double Ti[16], const double T0[16],
+                          const double A0[16], const double Ai[16], int chunk);
+/* nframes consecutive frames from host memory (depth = nframes*rows*cols, T = nframes*16), in order. */
+int er_tsdf_integrate_batch(er_tsdf* v, const uint16_t* depth, const double* T, int nframes);
+/* Same with the frames already resident in HBM (d_depth is a device pointer). */
+int er_tsdf_integrate_device(er_tsdf* v, const uint16_t* d_depth, const double* T, int nframes);
+/* Profiling variant of er_tsdf_integrate_device: brackets every kernel launch with CUDA events on the
+ * handle's stream and returns the summed device time of the touch (ScaleDepth + block activation) and
+ * integrate (IntegrateVolumeUnit) kernels over the nframes frames, in milliseconds. */
+int er_tsdf_profile_device(er_tsdf* v, const uint16_t* d_depth, const double* T, int nframes, float* touch_ms,
+                           float* integrate_ms);
+/* Frames handed to one fused launch by the batch calls (1 = one launch pair per frame). */
+int er_tsdf_set_fusion(er_tsdf* v, int frames_per_launch);
+int er_tsdf_sync(er_tsdf* v);
+
+/* Inspection for parity tests: allocated blocks, keyed like TSDFVolume::hash_key (TSDFVolume.h:62-64);
+ * sdf/weight are the two float[64^3] arrays of a TSDFVolumeUnit, k fastest (TSDFVolume.cpp:92). */
+int er_tsdf_num_blocks(er_tsdf* v, int* n);
+int er_tsdf_block_keys(er_tsdf* v, int* keys, int cap);
+int er_tsdf_read_block(er_tsdf* v, int key, float* sdf, float* weight);
+/* TSDFVolume::SaveWorld predicate (TSDFVolume.cpp:104-132): writes up to cap records x,y,z,intensity
+ * (global voxel indices as floats, tsdf) and the total count; order is unspecified as in the reference. */
+int er_tsdf_extract(er_tsdf* v, float* xyzi, size_t cap, size_t* n);
+
+/* Device-side timing on the handle's stream: record up to 16 events, read elapsed milliseconds. */
+int er_tsdf_event_record(er_tsdf* v, int slot);
+int er_tsdf_event_elapsed_ms(er_tsdf* v, int slot_a, int slot_b, float* ms);
+/* Number of kernel launches issued by this handle so far. */
+uint64_t er_tsdf_launch_count(er_tsdf* v);
+
+/* ================================================================================================
+ * ICP  (CCorresApp::{Registration,FindCorrespondence}, BuildCorrespondence/CorresApp.cpp:112-319)
+ * ============================================================================================== */
+typedef struct er_cloud er_cloud;
+typedef struct er_icp er_icp;
+
+/* One fragment (pcl::PointCloud<PointXYZRGBNormal> after the NaN-normal filter, CorresApp.cpp:93-98):
+ * xyz and normals as n*3 floats.  Builds the uniform-grid search structure that stands in for
+ * pcl::KdTreeFLANN::setInputCloud (CorresApp.cpp:148,253); cell_size must be >= every search radius
+ * later used against this cloud as a target. */
+er_cloud* er_cloud_upload(int device, const float* xyz, const float* normals, size_t n, double cell_size);
+void er_cloud_free(er_cloud* c);
+size_t er_cloud_size(const er_cloud* c);
+
+/* Gate of CCorresApp::Registration (CorresApp.cpp:250-264): cnt = #{k : NN^2(T*src_k) < dist^2}. */
+int er_icp_count_inliers(er_cloud* tgt, er_cloud* src, const double T[16], double dist, int* cnt);
+
+/* pcl::IterativeClosestPoint + TransformationEstimationPointToPlaneLLS as configured at
+ * CorresApp.cpp:295-306 (source = src, target = tgt, guess = Tinit cast to float).  fixed_iters != 0
+ * disables the convergence tests so that exactly max_iter iterations run (benchmark mode).
+ * Tout = final transformation (float math, widened), iters = iterations run, fitness = mean NN^2 of
+ * the last iteration's correspondences. */
+int er_icp_align(er_cloud* tgt, er_cloud* src, const double Tinit[16], double max_dist, int max_iter, double eps,
+                 int fixed_iters, double Tout[16], int* iters, double* fitness);
+
+/* Many pairs in flight on one device: pair p aligns src[src_idx[p]] onto tgt[tgt_idx[p]].
+ * Tinit/Tout = npairs*16 doubles; iters/fitness/converged may be NULL. */
+int er_icp_align_batch(er_cloud* const* clouds, int nclouds, const int* tgt_idx, const int* src_idx, int npairs,
+                       const double* Tinit, double max_dist, int max_iter, double eps, int fixed_iters,
+                       double* Tout, int* iters, double* fitness);
+
+/* CCorresApp::FindCorrespondence inner loop (CorresApp.cpp:145-161, 186-208): pairs = up to cap
+ * (target index, source index) rows in ascending source order, n = their number; info36 (optional) =
+ * sum A^T A over the correspondences on the untransformed source points, row-major 6x6. */
+int er_icp_correspondences(er_cloud* tgt, er_cloud* src, const double T[16], double dist, double normal_cos,
+                           int32_t* pairs, size_t cap, size_t* n, double info36[36]);
+
+/* Timing / accounting for the ICP path (events are recorded on the library's ICP stream of `device`). */
+int er_icp_event_record(int device, int slot);
+int er_icp_event_elapsed_ms(int device, int slot_a, int slot_b, float* ms);
+uint64_t er_icp_launch_count(int device);
+int er_icp_sync(int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELASTIC_B200_H_ */

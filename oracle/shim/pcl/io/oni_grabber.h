@@ -6,7 +6,9 @@
 // while it calls trigger() (Integrate/IntegrateApp.cpp:97-107).
 // With ER_SHIM_TIMING set, prints the wall time from the first trigger() to the
 // end-of-stream trigger() (= the time spent in Execute for all frames, without
-// the reference's 10 x 300 ms end-of-stream timeout).
+// the reference's 10 x 300 ms end-of-stream timeout).  With ER_SHIM_TIMING_FILE=<path>
+// it also writes the time of every trigger() call (seconds since the first, one per
+// line): consecutive differences are the per-frame processing times.
 #pragma once
 #include <chrono>
 #include <condition_variable>
@@ -41,7 +43,14 @@ class ONIGrabber : public Grabber {
     auto now = std::chrono::steady_clock::now();
     std::lock_guard<std::mutex> g(m_);
     if (!started_) { started_ = true; t0_ = now; }
+    if (!reported_) stamps_.push_back(std::chrono::duration<double>(now - t0_).count());
     if (next_ >= n_) {
+      if (!reported_ && std::getenv("ER_SHIM_TIMING_FILE")) {
+        if (std::FILE* tf = std::fopen(std::getenv("ER_SHIM_TIMING_FILE"), "w")) {
+          for (double t : stamps_) std::fprintf(tf, "%.9f\n", t);
+          std::fclose(tf);
+        }
+      }
       if (!reported_ && std::getenv("ER_SHIM_TIMING")) {
         double s = std::chrono::duration<double>(now - t0_).count();
         std::fprintf(stderr, "[shim] frames=%d elapsed_s=%.6f ms_per_frame=%.4f\n", n_, s, n_ ? 1e3 * s / n_ : 0.0);
@@ -73,6 +82,7 @@ class ONIGrabber : public Grabber {
   int n_, w_, h_, next_, pending_;
   bool quit_, started_, reported_;
   std::vector<uint16_t> buf_;
+  std::vector<double> stamps_;
   std::mutex m_;
   std::condition_variable cv_;
   std::thread worker_;
