@@ -215,6 +215,7 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=100)
     ap.add_argument("--ref-frames-per-step", type=int, default=8)
     ap.add_argument("--cpu-frames", type=int, default=120, help="frames timed for cpu_baseline (0 = skip)")
+    ap.add_argument("--fusion", type=int, default=32, help="frames per fused launch triple (1..32)")
     ap.add_argument("--no-icp", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -247,6 +248,7 @@ def main():
     # ---------------- value: frames resident in HBM
     d_frames = torch.from_numpy(frames_np.view(np.int16)).cuda(local)
     vol = capi.TSDFVolume(device=local, max_blocks=1024)
+    vol.set_fusion(args.fusion)
     torch.cuda.synchronize()
 
     assert need % F == 0, "--frames-per-step must divide the resident sequence so every step is one contiguous run"
@@ -282,37 +284,46 @@ def main():
 
     # ---------------- roofline: per-kernel time + exact updated-voxel count on the timed frames
     vol2 = capi.TSDFVolume(device=local, max_blocks=1024)
+    vol2.set_fusion(args.fusion)
     for s in range(args.warmup):
         idx = step_idx[s]
         vol2.integrate_device(d_frames.data_ptr() + int(idx[0]) * BYTES_PER_FRAME, poses[idx], F)
     vol2.set_stats(True)
     vol2.sync()
     st0 = vol2.stats()
-    t_touch = t_int = 0.0
+    t_touch = t_cls = t_int = 0.0
     for s in range(args.warmup, nsteps):
         idx = step_idx[s]
-        a, b = vol2.profile_device(d_frames.data_ptr() + int(idx[0]) * BYTES_PER_FRAME, poses[idx], F)
+        a, b, c = vol2.profile_device(d_frames.data_ptr() + int(idx[0]) * BYTES_PER_FRAME, poses[idx], F)
         t_touch += a
-        t_int += b
+        t_cls += b
+        t_int += c
     st1 = vol2.stats()
     n_prof = F * args.steps
+    fusion = args.fusion
+    n_launch = args.steps * ((F + fusion - 1) // fusion)          # integrate_kernel launches in the profiled pass
     upd = st1["updated_voxels"] - st0["updated_voxels"]
     blocks = st1["touched_blocks"] - st0["touched_blocks"]
-    alg_bytes_per_launch = (16.0 * upd + 2.0 * W * H * n_prof) / n_prof
-    int_s_per_launch = t_int * 1e-3 / n_prof
+    alg_bytes_per_launch = (16.0 * upd + 2.0 * W * H * n_prof) / n_launch
+    int_s_per_launch = t_int * 1e-3 / n_launch
     peak, peak_src = load_peaks()
     achieved = alg_bytes_per_launch / int_s_per_launch / 1e9
     roofline = {"bound": "hbm", "kernel": "integrate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch, "us_per_launch": int_s_per_launch * 1e6,
-                "touch_us_per_launch": t_touch * 1e3 / n_prof, "updated_voxels_per_frame": upd / n_prof,
-                "active_blocks_per_frame": blocks / n_prof,
-                "dense_bytes_per_launch": 16.0 * 262144 * blocks / n_prof + 2.0 * W * H}
+                "frames_per_launch": n_prof / n_launch,
+                "note": "algorithmic bytes = 16 B x updated voxels + 2 B x W x H per frame (SURVEY 8d); one launch "
+                        "applies a whole batch of frames to register-resident voxels, so achieved may exceed DRAM traffic",
+                "touch_us_per_frame": t_touch * 1e3 / n_prof, "classify_us_per_frame": t_cls * 1e3 / n_prof,
+                "integrate_us_per_frame": t_int * 1e3 / n_prof,
+                "updated_voxels_per_frame": upd / n_prof, "active_blocks_per_frame": blocks / n_prof,
+                "dense_bytes_per_frame": 16.0 * 262144 * blocks / n_prof + 2.0 * W * H}
     del vol2
 
     # ---------------- e2e: host buffers through the C ABI, H2D inside the timed region
     pinned = torch.from_numpy(frames_np.view(np.int16)).pin_memory()
     vol3 = capi.TSDFVolume(device=local, max_blocks=1024)
+    vol3.set_fusion(args.fusion)
     for s in range(args.warmup):
         idx = step_idx[s]
         vol3.integrate_ptr(pinned.data_ptr() + int(idx[0]) * BYTES_PER_FRAME, poses[idx], F)
@@ -351,7 +362,7 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "TSDF integrate: 1000 synthetic 640x480 frames, rigid trajectory, 512^3 @ 3/512 m "
                                    "(BASELINE configs[1])",
-                       "frames_per_step": F, "block_pool": 1024, "sharding": "independent volume per rank" if world > 1 else "single volume",
+                       "frames_per_step": F, "frames_per_launch": args.fusion, "block_pool": 1024, "sharding": "independent volume per rank" if world > 1 else "single volume",
                        "l2": "inputs larger than L2 (resident depth sequence %.0f MB + 2 GiB block pool); consecutive "
                              "frames legitimately reuse their active blocks through L2" % (need * BYTES_PER_FRAME / 1e6)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,

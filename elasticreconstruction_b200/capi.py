@@ -45,7 +45,7 @@ SIGNATURES = {
     "er_tsdf_integrate_ctr": (C.c_int, [C.c_void_p, c_u16p, c_dp, c_dp, c_dp, c_dp, C.c_int]),
     "er_tsdf_integrate_batch": (C.c_int, [C.c_void_p, c_u16p, c_dp, C.c_int]),
     "er_tsdf_integrate_device": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, C.c_int]),
-    "er_tsdf_profile_device": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, C.c_int, c_fp, c_fp]),
+    "er_tsdf_profile_device": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, C.c_int, c_fp, c_fp, c_fp]),
     "er_tsdf_set_fusion": (C.c_int, [C.c_void_p, C.c_int]),
     "er_tsdf_sync": (C.c_int, [C.c_void_p]),
     "er_tsdf_num_blocks": (C.c_int, [C.c_void_p, c_ip]),
@@ -201,11 +201,12 @@ class TSDFVolume:
         _check(lib().er_tsdf_integrate_device(self._h, C.c_void_p(device_ptr), _dp(Ts), n))
 
     def profile_device(self, device_ptr: int, T, n: int):
-        """Per-kernel device time over n resident frames: (touch_ms, integrate_ms), event-bracketed."""
+        """Per-kernel device time over n resident frames: (touch, classify, integrate) ms, event-bracketed."""
         Ts = np.ascontiguousarray(T, dtype=np.float64).reshape(-1, 16)
-        a, b = C.c_float(), C.c_float()
-        _check(lib().er_tsdf_profile_device(self._h, C.c_void_p(device_ptr), _dp(Ts), n, C.byref(a), C.byref(b)))
-        return a.value, b.value
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        _check(lib().er_tsdf_profile_device(self._h, C.c_void_p(device_ptr), _dp(Ts), n, C.byref(a), C.byref(b),
+                                            C.byref(c)))
+        return a.value, b.value, c.value
 
     def reproject(self, depth, Ti, T0, A0, Ai, grid_or_chunk, res=None, length=None):
         """CIntegrateApp::Reproject on one frame; returns the new depth image.

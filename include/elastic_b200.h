@@ -88,11 +88,13 @@ int er_tsdf_integrate_batch(er_tsdf* v, const uint16_t* depth, const double* T, 
 /* Same with the frames already resident in HBM (d_depth is a device pointer). */
 int er_tsdf_integrate_device(er_tsdf* v, const uint16_t* d_depth, const double* T, int nframes);
 /* Profiling variant of er_tsdf_integrate_device: brackets every kernel launch with CUDA events on the
- * handle's stream and returns the summed device time of the touch (ScaleDepth + block activation) and
- * integrate (IntegrateVolumeUnit) kernels over the nframes frames, in milliseconds. */
+ * handle's stream and returns the summed device time of the touch (ScaleDepth + block activation),
+ * classify (conservative sub-brick culling) and integrate (IntegrateVolumeUnit) kernels over the nframes
+ * frames, in milliseconds. */
 int er_tsdf_profile_device(er_tsdf* v, const uint16_t* d_depth, const double* T, int nframes, float* touch_ms,
-                           float* integrate_ms);
-/* Frames handed to one fused launch by the batch calls (1 = one launch pair per frame). */
+                           float* classify_ms, float* integrate_ms);
+/* Frames handed to one fused launch triple by the batch calls: 1..32, default 32.  A voxel is loaded once
+ * per batch and updated frame by frame in registers, in order. */
 int er_tsdf_set_fusion(er_tsdf* v, int frames_per_launch);
 int er_tsdf_sync(er_tsdf* v);
 

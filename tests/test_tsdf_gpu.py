@@ -119,6 +119,34 @@ def test_batch_and_device_paths_equal_per_frame(oracle):
     assert np.array_equal(ws[0].view(np.uint32), ws[2].view(np.uint32))
 
 
+@pytest.mark.parametrize("fusion", [1, 5, 32])
+def test_fusion_sizes_are_equivalent(oracle, fusion):
+    """Temporal fusion (several frames applied to register-resident voxels per launch) must not change a bit."""
+    sc = helpers.scene_room(n=12)
+    ovol = oracle.OracleTSDF()
+    for f in range(12):
+        ovol.integrate(sc["frames"][f], sc["traj"][f])
+    gvol = capi.TSDFVolume(max_blocks=512)
+    gvol.set_fusion(fusion)
+    gvol.integrate_batch(sc["frames"], sc["traj"][:12])
+    compare_blocks(ovol, gvol)
+
+
+def test_bumpy_room_many_frames(oracle):
+    """Longer sequence with a non-planar surface: exercises SKIP / ONE / FULL sub-brick classes side by side."""
+    sc = helpers.scene_room(n=40, total=200, bumps=True)
+    ovol = oracle.OracleTSDF()
+    gvol = capi.TSDFVolume(max_blocks=512)
+    gvol.set_stats(True)
+    upd = 0
+    for f in range(40):
+        ovol.integrate(sc["frames"][f], sc["traj"][f])
+        upd += ovol.last_updated_voxels()
+    gvol.integrate_batch(sc["frames"], sc["traj"][:40])
+    compare_blocks(ovol, gvol)
+    assert gvol.stats()["updated_voxels"] == upd
+
+
 def test_empty_frame_and_stats(oracle):
     vol = capi.TSDFVolume(max_blocks=64)
     vol.set_stats(True)
