@@ -284,3 +284,92 @@ class TSDFVolume:
 
     def launch_count(self) -> int:
         return int(lib().er_tsdf_launch_count(self._h))
+
+
+# ================================================================================================== ICP
+class Cloud:
+    """One fragment resident on the device: the reference's pointclouds_[i] (CorresApp.cpp:82-98) plus the
+    uniform-grid search structure standing in for pcl::KdTreeFLANN.  cell_size >= every radius used later."""
+
+    def __init__(self, xyz, normals, device: int = 0, cell_size: float = 0.03):
+        self.xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        self.normals = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        assert self.xyz.shape == self.normals.shape
+        self.device = device
+        h = lib().er_cloud_upload(device, _fp(self.xyz), _fp(self.normals), len(self.xyz), float(cell_size))
+        if not h:
+            raise ElasticError("er_cloud_upload failed: " + lib().er_last_error().decode("utf-8", "replace"))
+        self._h = C.c_void_p(h)
+
+    def __len__(self):
+        return int(lib().er_cloud_size(self._h))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().er_cloud_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def icp_count_inliers(tgt: Cloud, src: Cloud, T, dist: float) -> int:
+    """Gate of CCorresApp::Registration (CorresApp.cpp:250-264)."""
+    n = C.c_int()
+    _check(lib().er_icp_count_inliers(tgt._h, src._h, _dp(_mat(T)), float(dist), C.byref(n)))
+    return n.value
+
+
+def icp_align(tgt: Cloud, src: Cloud, Tinit, max_dist=0.03, max_iter=20, eps=1e-6, fixed_iters=False):
+    """pcl::IterativeClosestPoint as configured at CorresApp.cpp:295-306.  Returns (T, iterations, fitness)."""
+    out = np.empty(16, dtype=np.float64)
+    it = C.c_int()
+    fit = C.c_double()
+    _check(lib().er_icp_align(tgt._h, src._h, _dp(_mat(Tinit)), float(max_dist), int(max_iter), float(eps),
+                              int(bool(fixed_iters)), _dp(out), C.byref(it), C.byref(fit)))
+    return out.reshape(4, 4), it.value, fit.value
+
+
+def icp_align_batch(clouds, tgt_idx, src_idx, Tinit, max_dist=0.03, max_iter=20, eps=1e-6, fixed_iters=False):
+    """Many pairs in flight on one device (pair loop of CCorresApp::Registration, CorresApp.cpp:220)."""
+    n = len(tgt_idx)
+    arr = (C.c_void_p * len(clouds))(*[c._h for c in clouds])
+    ti = np.ascontiguousarray(tgt_idx, dtype=np.int32)
+    si = np.ascontiguousarray(src_idx, dtype=np.int32)
+    Ti = np.ascontiguousarray(Tinit, dtype=np.float64).reshape(n, 16)
+    out = np.empty((n, 16), dtype=np.float64)
+    its = np.empty(n, dtype=np.int32)
+    fit = np.empty(n, dtype=np.float64)
+    _check(lib().er_icp_align_batch(arr, len(clouds), ti.ctypes.data_as(c_ip), si.ctypes.data_as(c_ip), n, _dp(Ti),
+                                    float(max_dist), int(max_iter), float(eps), int(bool(fixed_iters)), _dp(out),
+                                    its.ctypes.data_as(c_ip), _dp(fit)))
+    return out.reshape(n, 4, 4), its, fit
+
+
+def icp_correspondences(tgt: Cloud, src: Cloud, T, dist=0.015, normal_cos=0.8660, want_info=True):
+    """FindCorrespondence inner loop (CorresApp.cpp:145-161,186-208): (pairs [m,2] = (target, source), info 6x6)."""
+    cap = len(src)
+    pairs = np.empty((max(cap, 1), 2), dtype=np.int32)
+    n = C.c_size_t()
+    info = np.zeros(36, dtype=np.float64) if want_info else None
+    _check(lib().er_icp_correspondences(tgt._h, src._h, _dp(_mat(T)), float(dist), float(normal_cos),
+                                        pairs.ctypes.data_as(c_i32p), cap, C.byref(n),
+                                        _dp(info) if want_info else None))
+    return pairs[: n.value].copy(), (info.reshape(6, 6) if want_info else None)
+
+
+def icp_event_record(device: int, slot: int):
+    _check(lib().er_icp_event_record(device, slot))
+
+
+def icp_event_elapsed_ms(device: int, a: int, b: int) -> float:
+    ms = C.c_float()
+    _check(lib().er_icp_event_elapsed_ms(device, a, b, C.byref(ms)))
+    return ms.value
+
+
+def icp_launch_count(device: int) -> int:
+    return int(lib().er_icp_launch_count(device))

@@ -1,15 +1,712 @@
-// er_icp.cu -- placeholder entry points so the ABI is complete while the ICP kernels are being written.
+// er_icp.cu -- pairwise point-to-plane ICP refinement on B200 (sm_100a): kernels + the er_cloud_*/er_icp_* C ABI.
+//
+// Replaces, behind include/elastic_b200.h, the inner loops of BuildCorrespondence:
+//   CCorresApp::Registration      BuildCorrespondence/CorresApp.cpp:212-319  (gate :250-264, ICP :295-312)
+//   CCorresApp::FindCorrespondence BuildCorrespondence/CorresApp.cpp:112-210 (:145-161 search, :186-208 information)
+// and the PCL 1.7 pieces those lines instantiate (not in the reference tree; semantics as restated in
+// oracle/icp_oracle.c, which is the definition this file is tested against):
+//   pcl::KdTreeFLANN::{setInputCloud,nearestKSearch}      -> uniform grid over the target + 3x3x3 cell search
+//   CorrespondenceEstimation::determineCorrespondences     -> icp_iter_kernel (search + gate)
+//   TransformationEstimationPointToPlaneLLS                -> icp_iter_kernel (rows, 6x6 normal equations, solve)
+//   IterativeClosestPoint::computeTransformation           -> one launch of icp_iter_kernel per iteration, no host sync
+//   DefaultConvergenceCriteria                             -> last CTA of each pair
+//   transformPointCloudWithNormals                         -> fused into the gate / correspondence kernels
+//
+// Data layout in HBM: per fragment the target role uses points sorted by grid cell as float4 (x, y, z, original
+// index) plus float4 normals in the same order and an int cell_start[] table; the source role uses the original
+// order (xyz, normals as float3 arrays).  One pair's working set is ~7 MB, far below the 126 MB L2, so the search
+// is latency/L2-bound, not HBM-bound; throughput comes from running many pairs per launch (blockIdx.y = pair).
+//
+// Numerics: squared distances and the incremental float transform use explicit round-to-nearest intrinsics in
+// the restated PCL/FLANN/Eigen order; the normal equations are accumulated in double and reduced in a fixed
+// order (per-thread -> warp shuffle tree -> per-CTA partial -> last CTA sums partials by index), so results are
+// reproducible run to run.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <new>
+#include <vector>
+
 #include "er_common.h"
-extern "C" {
-er_cloud* er_cloud_upload(int, const float*, const float*, size_t, double) { er::set_error("ICP path not built yet"); return nullptr; }
-void er_cloud_free(er_cloud*) {}
-size_t er_cloud_size(const er_cloud*) { return 0; }
-int er_icp_count_inliers(er_cloud*, er_cloud*, const double*, double, int*) { er::set_error("ICP path not built yet"); return ER_ERR_ARG; }
-int er_icp_align(er_cloud*, er_cloud*, const double*, double, int, double, int, double*, int*, double*) { er::set_error("ICP path not built yet"); return ER_ERR_ARG; }
-int er_icp_align_batch(er_cloud* const*, int, const int*, const int*, int, const double*, double, int, double, int, double*, int*, double*) { er::set_error("ICP path not built yet"); return ER_ERR_ARG; }
-int er_icp_correspondences(er_cloud*, er_cloud*, const double*, double, double, int32_t*, size_t, size_t*, double*) { er::set_error("ICP path not built yet"); return ER_ERR_ARG; }
-int er_icp_event_record(int, int) { return ER_ERR_ARG; }
-int er_icp_event_elapsed_ms(int, int, int, float*) { return ER_ERR_ARG; }
-uint64_t er_icp_launch_count(int) { return 0; }
-int er_icp_sync(int) { return ER_ERR_ARG; }
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kPtsPerThread = 4;
+constexpr int kPtsPerCta = kThreads * kPtsPerThread;
+constexpr int kAcc = 29;               // 21 (upper ATA) + 6 (ATb) + sum d^2 + count
+constexpr int kMaxEvents = 16;
+
+struct GridDev {
+  const float4* pts;      // sorted by cell: x, y, z, original index (int bits)
+  const float4* nrm;      // same order
+  const int* cell_start;  // ncell + 1
+  float org[3];
+  float inv_cell;
+  int dim[3];
+};
+
+struct PairState {
+  GridDev tgt;
+  float* cur;             // source points, transformed in place iteration by iteration (n_src * 3)
+  int n_src;
+  int nblocks;
+  double* partials;       // nblocks * kAcc
+  float Tinc[16];         // transform applied at the start of the next iteration
+  float fin[16];          // final_transformation_
+  double prev_mse, mse;
+  int iters, done, converged, cnt;
+  unsigned ticket;
+};
+
+// exact 1-NN inside the 27 cells around q; returns sorted position or -1.  Distance = ((dx*dx + dy*dy) + dz*dz)
+// in float (flann::L2_Simple order); ties go to the smallest original index.
+__device__ __forceinline__ int nn_search(const GridDev& g, float qx, float qy, float qz, float& best_d2) {
+  const int cx = (int)floorf(__fmul_rn(__fsub_rn(qx, g.org[0]), g.inv_cell));
+  const int cy = (int)floorf(__fmul_rn(__fsub_rn(qy, g.org[1]), g.inv_cell));
+  const int cz = (int)floorf(__fmul_rn(__fsub_rn(qz, g.org[2]), g.inv_cell));
+  int best = -1, best_idx = 0x7fffffff;
+  float bd = FLT_MAX;
+  const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1);
+  if (z0 <= z1) {
+    for (int ix = max(cx - 1, 0); ix <= min(cx + 1, g.dim[0] - 1); ix++) {
+      for (int iy = max(cy - 1, 0); iy <= min(cy + 1, g.dim[1] - 1); iy++) {
+        const int row = (ix * g.dim[1] + iy) * g.dim[2];
+        const int s0 = __ldg(&g.cell_start[row + z0]), s1 = __ldg(&g.cell_start[row + z1 + 1]);   // z cells are contiguous
+        for (int s = s0; s < s1; s++) {
+          const float4 p = __ldg(&g.pts[s]);
+          const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+          const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+          const int idx = __float_as_int(p.w);
+          if (d2 < bd || (d2 == bd && idx < best_idx)) { bd = d2; best = s; best_idx = idx; }
+        }
+      }
+    }
+  }
+  best_d2 = bd;
+  return best;
 }
+
+// 6x6 solve by Gaussian elimination with partial pivoting (same algorithm as the oracle's solve6)
+__device__ bool solve6(double* A, double* b, double* x) {
+  for (int col = 0; col < 6; col++) {
+    int piv = col;
+    double big = fabs(A[col * 6 + col]);
+    for (int r = col + 1; r < 6; r++)
+      if (fabs(A[r * 6 + col]) > big) { big = fabs(A[r * 6 + col]); piv = r; }
+    if (big == 0.0) return false;
+    if (piv != col) {
+      for (int c = 0; c < 6; c++) { const double t = A[col * 6 + c]; A[col * 6 + c] = A[piv * 6 + c]; A[piv * 6 + c] = t; }
+      const double t = b[col]; b[col] = b[piv]; b[piv] = t;
+    }
+    for (int r = col + 1; r < 6; r++) {
+      const double f = __ddiv_rn(A[r * 6 + col], A[col * 6 + col]);
+      for (int c = col; c < 6; c++) A[r * 6 + c] = __dsub_rn(A[r * 6 + c], __dmul_rn(f, A[col * 6 + c]));
+      b[r] = __dsub_rn(b[r], __dmul_rn(f, b[col]));
+    }
+  }
+  for (int r = 5; r >= 0; r--) {
+    double s = b[r];
+    for (int c = r + 1; c < 6; c++) s = __dsub_rn(s, __dmul_rn(A[r * 6 + c], x[c]));
+    x[r] = __ddiv_rn(s, A[r * 6 + r]);
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// icp_iter_kernel: one ICP iteration for every pair of the batch (grid = (CTAs per pair, pairs)).
+//   1. input_transformed = T_inc * input_transformed   (float, Eigen order; T_inc of the previous iteration)
+//   2. 1-NN in the target grid, keep unless dist^2 > max_dist^2   (determineCorrespondences)
+//   3. point-to-plane row [s x n, n], d = n.(t - s), accumulate A^T A / A^T b in double   (LLS)
+//   4. CTA partial -> global; the pair's last CTA sums the partials in index order, solves the 6x6 system,
+//      builds T_inc = Rz Ry Rx + t, updates final = T_inc * final and evaluates the convergence criteria.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) icp_iter_kernel(PairState* states, double max_d2, int max_iter, double eps,
+                                                            int fixed_iters) {
+  PairState& S = states[blockIdx.y];
+  if (blockIdx.x >= S.nblocks || S.done) return;
+  __shared__ double s_part[kThreads / 32][kAcc];
+  __shared__ bool s_last;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float M[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) M[i] = S.Tinc[i];
+  const GridDev g = S.tgt;
+  double acc[kAcc];
+#pragma unroll
+  for (int i = 0; i < kAcc; i++) acc[i] = 0.0;
+
+  const int base = blockIdx.x * kPtsPerCta;
+#pragma unroll 1
+  for (int it = 0; it < kPtsPerThread; it++) {
+    const int k = base + it * kThreads + tid;
+    if (k >= S.n_src) break;
+    float* cp = S.cur + 3 * (size_t)k;
+    const float x = cp[0], y = cp[1], z = cp[2];
+    // Matrix4f * (x, y, z, 1): ((m0*x + m1*y) + m2*z) + m3*1
+    const float sx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[0], x), __fmul_rn(M[1], y)), __fmul_rn(M[2], z)), M[3]);
+    const float sy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[4], x), __fmul_rn(M[5], y)), __fmul_rn(M[6], z)), M[7]);
+    const float sz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[8], x), __fmul_rn(M[9], y)), __fmul_rn(M[10], z)), M[11]);
+    cp[0] = sx; cp[1] = sy; cp[2] = sz;
+    float d2;
+    const int m = nn_search(g, sx, sy, sz, d2);
+    if (m >= 0 && !((double)d2 > max_d2)) {
+      const float4 t = __ldg(&g.pts[m]);
+      const float4 nn = __ldg(&g.nrm[m]);
+      const float dx = t.x, dy = t.y, dz = t.z, nx = nn.x, ny = nn.y, nz = nn.z;
+      acc[27] += (double)d2;
+      acc[28] += 1.0;
+      if (isfinite(sx) && isfinite(sy) && isfinite(sz) && isfinite(dx) && isfinite(dy) && isfinite(dz) && isfinite(nx) &&
+          isfinite(ny) && isfinite(nz)) {
+        // float expressions widened afterwards, as in PCL's estimateRigidTransformation (float operands)
+        const double a = (double)__fsub_rn(__fmul_rn(nz, sy), __fmul_rn(ny, sz));
+        const double b = (double)__fsub_rn(__fmul_rn(nx, sz), __fmul_rn(nz, sx));
+        const double c = (double)__fsub_rn(__fmul_rn(ny, sx), __fmul_rn(nx, sy));
+        float df = __fadd_rn(__fadd_rn(__fmul_rn(nx, dx), __fmul_rn(ny, dy)), __fmul_rn(nz, dz));
+        df = __fsub_rn(__fsub_rn(__fsub_rn(df, __fmul_rn(nx, sx)), __fmul_rn(ny, sy)), __fmul_rn(nz, sz));
+        const double d = (double)df;
+        const double dnx = (double)nx, dny = (double)ny, dnz = (double)nz;
+        acc[0] += a * a;   acc[1] += a * b;   acc[2] += a * c;   acc[3] += a * dnx;  acc[4] += a * dny;  acc[5] += a * dnz;
+        acc[6] += b * b;   acc[7] += b * c;   acc[8] += b * dnx; acc[9] += b * dny;  acc[10] += b * dnz;
+        acc[11] += c * c;  acc[12] += c * dnx; acc[13] += c * dny; acc[14] += c * dnz;
+        acc[15] += (double)__fmul_rn(nx, nx); acc[16] += (double)__fmul_rn(nx, ny); acc[17] += (double)__fmul_rn(nx, nz);
+        acc[18] += (double)__fmul_rn(ny, ny); acc[19] += (double)__fmul_rn(ny, nz);
+        acc[20] += (double)__fmul_rn(nz, nz);
+        acc[21] += a * d;  acc[22] += b * d;  acc[23] += c * d;  acc[24] += dnx * d;  acc[25] += dny * d;  acc[26] += dnz * d;
+      }
+    }
+  }
+  // ---- CTA reduction (fixed tree)
+#pragma unroll
+  for (int i = 0; i < kAcc; i++) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) s_part[warp][i] = v;
+  }
+  __syncthreads();
+  if (tid < kAcc) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < kThreads / 32; w++) v += s_part[w][tid];
+    S.partials[(size_t)blockIdx.x * kAcc + tid] = v;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(&S.ticket, 1u) == (unsigned)(S.nblocks - 1));
+  __syncthreads();
+  if (!s_last) return;
+  // ---- the pair's last CTA: finish the iteration
+  __shared__ double s_sum[kAcc];
+  if (tid < kAcc) {
+    double v = 0.0;
+    for (int b = 0; b < S.nblocks; b++) v += __ldcg(&S.partials[(size_t)b * kAcc + tid]);
+    s_sum[tid] = v;
+  }
+  __syncthreads();
+  if (tid != 0) return;
+  S.ticket = 0;
+  const int cnt = (int)s_sum[28];
+  S.cnt = cnt;
+  if (cnt < 3) { S.done = 1; S.converged = 0; return; }          // min_number_correspondences_
+  const double mse = s_sum[27] / (double)cnt;
+  S.mse = mse;
+  double A[36], rhs[6], x[6];
+  {
+    int q = 0;
+    for (int r = 0; r < 6; r++)
+      for (int c = r; c < 6; c++) { A[r * 6 + c] = s_sum[q]; A[c * 6 + r] = s_sum[q]; q++; }
+    for (int r = 0; r < 6; r++) rhs[r] = s_sum[21 + r];
+  }
+  if (!solve6(A, rhs, x)) { S.done = 1; S.converged = 0; return; }
+  // constructTransformationMatrix(alpha, beta, gamma, tx, ty, tz)
+  const double al = x[0], be = x[1], ga = x[2];
+  const double sa = sin(al), ca = cos(al), sb = sin(be), cb = cos(be), sg = sin(ga), cg = cos(ga);
+  float T[16];
+  T[0] = (float)__dmul_rn(cg, cb);
+  T[1] = (float)__dadd_rn(__dmul_rn(-sg, ca), __dmul_rn(__dmul_rn(cg, sb), sa));
+  T[2] = (float)__dadd_rn(__dmul_rn(sg, sa), __dmul_rn(__dmul_rn(cg, sb), ca));
+  T[4] = (float)__dmul_rn(sg, cb);
+  T[5] = (float)__dadd_rn(__dmul_rn(cg, ca), __dmul_rn(__dmul_rn(sg, sb), sa));
+  T[6] = (float)__dadd_rn(__dmul_rn(-cg, sa), __dmul_rn(__dmul_rn(sg, sb), ca));
+  T[8] = (float)(-sb);
+  T[9] = (float)__dmul_rn(cb, sa);
+  T[10] = (float)__dmul_rn(cb, ca);
+  T[3] = (float)x[3]; T[7] = (float)x[4]; T[11] = (float)x[5];
+  T[12] = T[13] = T[14] = 0.0f; T[15] = 1.0f;
+  float F[16];
+  for (int r = 0; r < 4; r++)
+    for (int c = 0; c < 4; c++)
+      F[r * 4 + c] = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(T[r * 4], S.fin[c]), __fmul_rn(T[r * 4 + 1], S.fin[4 + c])),
+                                         __fmul_rn(T[r * 4 + 2], S.fin[8 + c])), __fmul_rn(T[r * 4 + 3], S.fin[12 + c]));
+  for (int i = 0; i < 16; i++) { S.fin[i] = F[i]; S.Tinc[i] = T[i]; }
+  const int iters = ++S.iters;
+  // DefaultConvergenceCriteria::hasConverged
+  if (iters >= max_iter) { S.done = 1; S.converged = 1; return; }
+  if (!fixed_iters) {
+    const double cos_angle = 0.5 * ((double)T[0] + (double)T[5] + (double)T[10] - 1.0);
+    const double tsq = (double)T[3] * (double)T[3] + (double)T[7] * (double)T[7] + (double)T[11] * (double)T[11];
+    if (cos_angle >= 1.0 - eps && tsq <= eps) { S.done = 1; S.converged = 1; return; }
+    if (fabs(mse - S.prev_mse) < 1e-12) { S.done = 1; S.converged = 1; return; }
+    S.prev_mse = mse;
+  }
+}
+
+// pcl::transformPointCloudWithNormals in double, narrowed to float (CorresApp.cpp:145,250)
+struct XformD { double T[12]; };
+
+__device__ __forceinline__ void xform_point(const XformD& X, const float* p, float& ox, float& oy, float& oz) {
+  const double x = p[0], y = p[1], z = p[2];
+  ox = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(X.T[0], x), __dmul_rn(X.T[1], y)), __dmul_rn(X.T[2], z)), X.T[3]);
+  oy = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(X.T[4], x), __dmul_rn(X.T[5], y)), __dmul_rn(X.T[6], z)), X.T[7]);
+  oz = (float)__dadd_rn(__dadd_rn(__dadd_rn(__dmul_rn(X.T[8], x), __dmul_rn(X.T[9], y)), __dmul_rn(X.T[10], z)), X.T[11]);
+}
+__device__ __forceinline__ void xform_normal(const XformD& X, const float* n, float& ox, float& oy, float& oz) {
+  const double x = n[0], y = n[1], z = n[2];
+  ox = (float)__dadd_rn(__dadd_rn(__dmul_rn(X.T[0], x), __dmul_rn(X.T[1], y)), __dmul_rn(X.T[2], z));
+  oy = (float)__dadd_rn(__dadd_rn(__dmul_rn(X.T[4], x), __dmul_rn(X.T[5], y)), __dmul_rn(X.T[6], z));
+  oz = (float)__dadd_rn(__dadd_rn(__dmul_rn(X.T[8], x), __dmul_rn(X.T[9], y)), __dmul_rn(X.T[10], z));
+}
+
+// gate of CCorresApp::Registration (CorresApp.cpp:257-264)
+__global__ void __launch_bounds__(kThreads) count_inliers_kernel(GridDev g, const float* __restrict__ src_xyz, int n,
+                                                                 XformD X, double d2max, int* count) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  bool in = false;
+  if (k < n) {
+    float qx, qy, qz, d2;
+    xform_point(X, src_xyz + 3 * (size_t)k, qx, qy, qz);
+    in = nn_search(g, qx, qy, qz, d2) >= 0 && (double)d2 < d2max;
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, in);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, __popc(m));
+}
+
+// FindCorrespondence search (CorresApp.cpp:145-161): match[k] = original target index or -1
+__global__ void __launch_bounds__(kThreads) correspond_kernel(GridDev g, const float* __restrict__ src_xyz,
+                                                              const float* __restrict__ src_nrm, int n, XformD X,
+                                                              double d2max, double ncos, int* __restrict__ match,
+                                                              int* __restrict__ cta_count) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  int mt = -1;
+  if (k < n) {
+    float qx, qy, qz, d2;
+    xform_point(X, src_xyz + 3 * (size_t)k, qx, qy, qz);
+    const int m = nn_search(g, qx, qy, qz, d2);
+    if (m >= 0 && (double)d2 < d2max) {
+      float nx, ny, nz;
+      xform_normal(X, src_nrm + 3 * (size_t)k, nx, ny, nz);
+      const float4 tn = __ldg(&g.nrm[m]);
+      const float dot = __fadd_rn(__fadd_rn(__fmul_rn(tn.x, nx), __fmul_rn(tn.y, ny)), __fmul_rn(tn.z, nz));   // NormalDot
+      if ((double)dot > ncos) mt = __float_as_int(__ldg(&g.pts[m]).w);
+    }
+    match[k] = mt;
+  }
+  const int c = __syncthreads_count(mt >= 0);
+  if (threadIdx.x == 0) cta_count[blockIdx.x] = c;
+}
+
+// exclusive scan of the per-CTA counts (a few hundred entries) by one CTA; total -> offsets[nblk]
+__global__ void scan_counts_kernel(const int* __restrict__ counts, int* __restrict__ offsets, int nblk) {
+  __shared__ int s_carry;
+  __shared__ int s_w[32];
+  if (threadIdx.x == 0) s_carry = 0;
+  __syncthreads();
+  for (int base = 0; base < nblk; base += blockDim.x) {
+    const int i = base + threadIdx.x;
+    const int v = (i < nblk) ? counts[i] : 0;
+    int x = v;
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_w[w] = x;
+    __syncthreads();
+    if (w == 0) {
+      int t = (lane < (int)(blockDim.x >> 5)) ? s_w[lane] : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xffffffffu, t, o); if (lane >= o) t += y; }
+      s_w[lane] = t;
+    }
+    __syncthreads();
+    const int incl = x + (w > 0 ? s_w[w - 1] : 0) + s_carry;
+    if (i < nblk) offsets[i] = incl - v;
+    __syncthreads();
+    if (threadIdx.x == blockDim.x - 1) s_carry = incl;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) offsets[nblk] = s_carry;
+}
+
+// ordered compaction (ascending source index, CorresApp.cpp:157) + information matrix sums (CorresApp.cpp:186-208)
+__global__ void __launch_bounds__(kThreads) compact_kernel(const int* __restrict__ match, const int* __restrict__ offsets,
+                                                           const float* __restrict__ src_xyz, int n, int32_t* __restrict__ pairs,
+                                                           size_t cap, double* __restrict__ info_acc) {
+  __shared__ int s_w[kThreads / 32];
+  __shared__ double s_acc[kThreads / 32][12];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int mt = (k < n) ? match[k] : -1;
+  const unsigned bal = __ballot_sync(0xffffffffu, mt >= 0);
+  if (lane == 0) s_w[w] = __popc(bal);
+  __syncthreads();
+  int before = 0;
+  for (int q = 0; q < w; q++) before += s_w[q];
+  double acc[12];
+#pragma unroll
+  for (int i = 0; i < 12; i++) acc[i] = 0.0;
+  if (mt >= 0) {
+    const size_t pos = (size_t)offsets[blockIdx.x] + before + __popc(bal & ((1u << lane) - 1));
+    if (pairs && pos < cap) { pairs[2 * pos] = mt; pairs[2 * pos + 1] = k; }
+    if (info_acc) {
+      // A = [I | 0 2sz -2sy; -2sz 0 2sx; 2sy -2sx 0]; entry (r,c) of A^T A = (A0r*A0c + A1r*A1c) + A2r*A2c in double
+      const double sx2 = (double)(2.0f * src_xyz[3 * (size_t)k]), sy2 = (double)(2.0f * src_xyz[3 * (size_t)k + 1]),
+                   sz2 = (double)(2.0f * src_xyz[3 * (size_t)k + 2]);
+      acc[0] = 1.0;                                  // (0,0) = (1,1) = (2,2)
+      acc[1] = sz2;  acc[2] = -sy2;                  // (0,4), (0,5)
+      acc[3] = -sz2; acc[4] = sx2;                   // (1,3), (1,5)
+      acc[5] = sy2;  acc[6] = -sx2;                  // (2,3), (2,4)
+      acc[7] = __dadd_rn(__dmul_rn(-sz2, -sz2), __dmul_rn(sy2, sy2));    // (3,3) = (0 + (-2sz)^2) + (2sy)^2
+      acc[8] = __dmul_rn(sy2, -sx2);                                      // (3,4) = (0 + 0) + (2sy)(-2sx)
+      acc[9] = __dmul_rn(-sz2, sx2);                                      // (3,5) = (0 + (-2sz)(2sx)) + 0
+      acc[10] = __dadd_rn(__dmul_rn(sz2, sz2), __dmul_rn(-sx2, -sx2));   // (4,4) = ((2sz)^2 + 0) + (-2sx)^2
+      acc[11] = __dmul_rn(sz2, -sy2);                                     // (4,5) = ((2sz)(-2sy) + 0) + 0
+      // (5,5) = ((-2sy)^2 + (2sx)^2) + 0 is accumulated from the same operands below
+    }
+  }
+  if (info_acc) {
+    double a55 = 0.0;
+    if (mt >= 0) {
+      const double sx2 = (double)(2.0f * src_xyz[3 * (size_t)k]), sy2 = (double)(2.0f * src_xyz[3 * (size_t)k + 1]);
+      a55 = __dadd_rn(__dmul_rn(-sy2, -sy2), __dmul_rn(sx2, sx2));
+    }
+    // reduce 13 values: reuse acc[0..11] + a55
+#pragma unroll
+    for (int i = 0; i < 12; i++) {
+      double v = acc[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+      if (lane == 0) s_acc[w][i] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) a55 += __shfl_down_sync(0xffffffffu, a55, o);
+    __syncthreads();
+    if (threadIdx.x < 12) {
+      double v = 0.0;
+      for (int q = 0; q < kThreads / 32; q++) v += s_acc[q][threadIdx.x];
+      if (v != 0.0) atomicAdd(&info_acc[threadIdx.x], v);
+    }
+    if (lane == 0 && a55 != 0.0) atomicAdd(&info_acc[12], a55);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct IcpCtx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t events[kMaxEvents] = {};
+  uint64_t launches = 0;
+};
+std::mutex g_ctx_mu;
+std::map<int, IcpCtx*> g_ctx;
+
+IcpCtx* get_ctx(int device) {
+  std::lock_guard<std::mutex> lk(g_ctx_mu);
+  auto it = g_ctx.find(device);
+  if (it != g_ctx.end()) return it->second;
+  if (cudaSetDevice(device) != cudaSuccess) return nullptr;
+  IcpCtx* c = new IcpCtx();
+  c->device = device;
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return nullptr; }
+  for (int i = 0; i < kMaxEvents; i++) cudaEventCreate(&c->events[i]);
+  g_ctx[device] = c;
+  return c;
+}
+
+}  // namespace
+
+struct er_cloud {
+  int device = 0;
+  size_t n = 0;
+  float4* d_pts = nullptr;
+  float4* d_nrm = nullptr;
+  int* d_cell_start = nullptr;
+  float* d_xyz = nullptr;      // original order
+  float* d_nrm_orig = nullptr;
+  GridDev grid{};
+  double cell = 0;
+};
+
+extern "C" {
+
+er_cloud* er_cloud_upload(int device, const float* xyz, const float* normals, size_t n, double cell_size) {
+  if (!xyz || !normals || !(cell_size > 0)) { er::set_error("er_cloud_upload: bad arguments"); return nullptr; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    er::set_error("er_cloud_upload: CUDA device %d not available (%d devices); this library has no CPU path", device, ndev);
+    return nullptr;
+  }
+  if (!get_ctx(device)) { er::set_error("er_cloud_upload: cannot create a stream on device %d", device); return nullptr; }
+  er_cloud* c = new (std::nothrow) er_cloud();
+  if (!c) return nullptr;
+  c->device = device;
+  c->n = n;
+  // ---- uniform grid over the bounding box (host side; done once per fragment, outside the iteration loop)
+  float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  for (size_t i = 0; i < n; i++)
+    for (int a = 0; a < 3; a++) {
+      const float v = xyz[3 * i + a];
+      if (v < lo[a]) lo[a] = v;
+      if (v > hi[a]) hi[a] = v;
+    }
+  if (n == 0) for (int a = 0; a < 3; a++) lo[a] = hi[a] = 0.f;
+  double cell = cell_size * 1.001;     // strictly larger than any admissible radius: neighbours differ by <= 1 cell
+  int dim[3];
+  for (;;) {
+    double cells = 1;
+    for (int a = 0; a < 3; a++) { dim[a] = (int)std::floor((hi[a] - lo[a]) / cell) + 1; cells *= dim[a]; }
+    if (cells <= 64e6) break;
+    cell *= 2;
+  }
+  c->cell = cell;
+  GridDev& g = c->grid;
+  g.inv_cell = (float)(1.0 / cell);
+  for (int a = 0; a < 3; a++) { g.org[a] = lo[a]; g.dim[a] = dim[a]; }
+  const size_t ncell = (size_t)dim[0] * dim[1] * dim[2];
+  std::vector<int> cell_start(ncell + 1, 0), cid(n);
+  auto cell_of = [&](float v, int a) {
+    int i = (int)std::floor((v - g.org[a]) * g.inv_cell);
+    return std::min(std::max(i, 0), dim[a] - 1);
+  };
+  for (size_t i = 0; i < n; i++) {
+    cid[i] = (cell_of(xyz[3 * i], 0) * dim[1] + cell_of(xyz[3 * i + 1], 1)) * dim[2] + cell_of(xyz[3 * i + 2], 2);
+    cell_start[cid[i] + 1]++;
+  }
+  for (size_t k = 0; k < ncell; k++) cell_start[k + 1] += cell_start[k];
+  std::vector<int> fill(cell_start.begin(), cell_start.end() - 1);
+  std::vector<float4> pts(n ? n : 1), nrm(n ? n : 1);
+  for (size_t i = 0; i < n; i++) {
+    const int pos = fill[cid[i]]++;
+    int idx = (int)i;
+    float w;
+    std::memcpy(&w, &idx, sizeof w);
+    pts[pos] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], w);
+    nrm[pos] = make_float4(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2], 0.f);
+  }
+  cudaError_t e = cudaSetDevice(device);
+  auto up = [&](void** dptr, const void* src, size_t bytes) {
+    if (e != cudaSuccess) return;
+    e = cudaMalloc(dptr, bytes ? bytes : 16);
+    if (e == cudaSuccess && bytes) e = cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
+  };
+  up((void**)&c->d_pts, pts.data(), sizeof(float4) * n);
+  up((void**)&c->d_nrm, nrm.data(), sizeof(float4) * n);
+  up((void**)&c->d_cell_start, cell_start.data(), sizeof(int) * (ncell + 1));
+  up((void**)&c->d_xyz, xyz, sizeof(float) * 3 * n);
+  up((void**)&c->d_nrm_orig, normals, sizeof(float) * 3 * n);
+  if (e != cudaSuccess) {
+    er::set_error("er_cloud_upload: %s", cudaGetErrorString(e));
+    er_cloud_free(c);
+    return nullptr;
+  }
+  g.pts = c->d_pts; g.nrm = c->d_nrm; g.cell_start = c->d_cell_start;
+  return c;
+}
+
+void er_cloud_free(er_cloud* c) {
+  if (!c) return;
+  cudaSetDevice(c->device);
+  cudaFree(c->d_pts); cudaFree(c->d_nrm); cudaFree(c->d_cell_start); cudaFree(c->d_xyz); cudaFree(c->d_nrm_orig);
+  delete c;
+}
+
+size_t er_cloud_size(const er_cloud* c) { return c ? c->n : 0; }
+
+int er_icp_count_inliers(er_cloud* tgt, er_cloud* src, const double T[16], double dist, int* cnt) {
+  ER_ARG(tgt && src && T && cnt && tgt->device == src->device, "count_inliers: bad arguments");
+  ER_ARG(dist <= tgt->cell, "count_inliers: dist exceeds the target cloud's grid cell size");
+  IcpCtx* ctx = get_ctx(tgt->device);
+  ER_ARG(ctx, "no CUDA context");
+  ER_CUDA(cudaSetDevice(tgt->device));
+  int* d_cnt = nullptr;
+  ER_CUDA(cudaMalloc((void**)&d_cnt, sizeof(int)));
+  ER_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int), ctx->stream));
+  XformD X;
+  for (int i = 0; i < 12; i++) X.T[i] = T[i];
+  const int n = (int)src->n;
+  if (n > 0) {
+    count_inliers_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(tgt->grid, src->d_xyz, n, X, dist * dist, d_cnt);
+    ctx->launches++;
+  }
+  cudaError_t e = cudaMemcpyAsync(cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_cnt);
+  if (e != cudaSuccess) { er::set_error("count_inliers: %s", cudaGetErrorString(e)); return ER_ERR_CUDA; }
+  return ER_OK;
+}
+
+int er_icp_align_batch(er_cloud* const* clouds, int nclouds, const int* tgt_idx, const int* src_idx, int npairs,
+                       const double* Tinit, double max_dist, int max_iter, double eps, int fixed_iters, double* Tout,
+                       int* iters, double* fitness) {
+  ER_ARG(clouds && nclouds > 0 && tgt_idx && src_idx && npairs >= 0 && Tinit && Tout && max_iter >= 1, "align_batch: bad arguments");
+  if (npairs == 0) return ER_OK;
+  const int device = clouds[0]->device;
+  IcpCtx* ctx = get_ctx(device);
+  ER_ARG(ctx, "no CUDA context");
+  ER_CUDA(cudaSetDevice(device));
+  std::vector<PairState> st((size_t)npairs);
+  size_t cur_floats = 0, part_doubles = 0;
+  int max_blocks = 1;
+  for (int p = 0; p < npairs; p++) {
+    ER_ARG(tgt_idx[p] >= 0 && tgt_idx[p] < nclouds && src_idx[p] >= 0 && src_idx[p] < nclouds, "align_batch: cloud index out of range");
+    const er_cloud* t = clouds[tgt_idx[p]];
+    const er_cloud* s = clouds[src_idx[p]];
+    ER_ARG(t && s && t->device == device && s->device == device, "align_batch: clouds must live on one device");
+    ER_ARG(max_dist <= t->cell, "align_batch: max_dist exceeds the target cloud's grid cell size");
+    const int nb = std::max(1, (int)((s->n + kPtsPerCta - 1) / kPtsPerCta));
+    max_blocks = std::max(max_blocks, nb);
+    cur_floats += 3 * s->n;
+    part_doubles += (size_t)nb * kAcc;
+  }
+  float* d_cur = nullptr;
+  double* d_part = nullptr;
+  PairState* d_st = nullptr;
+  ER_CUDA(cudaMalloc((void**)&d_cur, sizeof(float) * std::max<size_t>(cur_floats, 4)));
+  ER_CUDA(cudaMalloc((void**)&d_part, sizeof(double) * part_doubles));
+  ER_CUDA(cudaMalloc((void**)&d_st, sizeof(PairState) * (size_t)npairs));
+  size_t co = 0, po = 0;
+  for (int p = 0; p < npairs; p++) {
+    const er_cloud* t = clouds[tgt_idx[p]];
+    const er_cloud* s = clouds[src_idx[p]];
+    PairState& S = st[(size_t)p];
+    std::memset(&S, 0, sizeof S);
+    S.tgt = t->grid;
+    S.cur = d_cur + co;
+    S.n_src = (int)s->n;
+    S.nblocks = std::max(1, (int)((s->n + kPtsPerCta - 1) / kPtsPerCta));
+    S.partials = d_part + po;
+    for (int i = 0; i < 16; i++) S.Tinc[i] = S.fin[i] = (float)Tinit[16 * (size_t)p + i];   // guess.cast<float>()
+    S.prev_mse = DBL_MAX;
+    if (s->n) cudaMemcpyAsync(S.cur, s->d_xyz, sizeof(float) * 3 * s->n, cudaMemcpyDeviceToDevice, ctx->stream);
+    co += 3 * s->n;
+    po += (size_t)S.nblocks * kAcc;
+  }
+  cudaError_t e = cudaMemcpyAsync(d_st, st.data(), sizeof(PairState) * (size_t)npairs, cudaMemcpyHostToDevice, ctx->stream);
+  const double max_d2 = max_dist * max_dist;
+  const dim3 grid((unsigned)max_blocks, (unsigned)npairs);
+  for (int it = 0; it < max_iter && e == cudaSuccess; it++) {
+    icp_iter_kernel<<<grid, kThreads, 0, ctx->stream>>>(d_st, max_d2, max_iter, eps, fixed_iters);
+    ctx->launches++;
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(st.data(), d_st, sizeof(PairState) * (size_t)npairs, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_cur); cudaFree(d_part); cudaFree(d_st);
+  if (e != cudaSuccess) { er::set_error("align_batch: %s", cudaGetErrorString(e)); return ER_ERR_CUDA; }
+  for (int p = 0; p < npairs; p++) {
+    for (int i = 0; i < 16; i++) Tout[16 * (size_t)p + i] = (double)st[(size_t)p].fin[i];    // .cast<double>(), CorresApp.cpp:312
+    if (iters) iters[p] = st[(size_t)p].iters;
+    if (fitness) fitness[p] = st[(size_t)p].mse;
+  }
+  return ER_OK;
+}
+
+int er_icp_align(er_cloud* tgt, er_cloud* src, const double Tinit[16], double max_dist, int max_iter, double eps,
+                 int fixed_iters, double Tout[16], int* iters, double* fitness) {
+  ER_ARG(tgt && src, "align: null cloud");
+  er_cloud* cl[2] = {tgt, src};
+  const int ti = 0, si = 1;
+  return er_icp_align_batch(cl, 2, &ti, &si, 1, Tinit, max_dist, max_iter, eps, fixed_iters, Tout, iters, fitness);
+}
+
+int er_icp_correspondences(er_cloud* tgt, er_cloud* src, const double T[16], double dist, double normal_cos, int32_t* pairs,
+                           size_t cap, size_t* n_out, double info36[36]) {
+  ER_ARG(tgt && src && T && n_out && tgt->device == src->device, "correspondences: bad arguments");
+  ER_ARG(dist <= tgt->cell, "correspondences: dist exceeds the target cloud's grid cell size");
+  IcpCtx* ctx = get_ctx(tgt->device);
+  ER_ARG(ctx, "no CUDA context");
+  ER_CUDA(cudaSetDevice(tgt->device));
+  const int n = (int)src->n;
+  *n_out = 0;
+  if (info36) std::memset(info36, 0, sizeof(double) * 36);
+  if (n == 0) return ER_OK;
+  const int nblk = (n + kThreads - 1) / kThreads;
+  int *d_match = nullptr, *d_counts = nullptr, *d_off = nullptr;
+  int32_t* d_pairs = nullptr;
+  double* d_info = nullptr;
+  ER_CUDA(cudaMalloc((void**)&d_match, sizeof(int) * (size_t)n));
+  ER_CUDA(cudaMalloc((void**)&d_counts, sizeof(int) * (size_t)nblk));
+  ER_CUDA(cudaMalloc((void**)&d_off, sizeof(int) * (size_t)(nblk + 1)));
+  const size_t pcap = pairs ? std::min(cap, (size_t)n) : 0;
+  if (pcap) ER_CUDA(cudaMalloc((void**)&d_pairs, sizeof(int32_t) * 2 * pcap));
+  if (info36) {
+    ER_CUDA(cudaMalloc((void**)&d_info, sizeof(double) * 13));
+    ER_CUDA(cudaMemsetAsync(d_info, 0, sizeof(double) * 13, ctx->stream));
+  }
+  XformD X;
+  for (int i = 0; i < 12; i++) X.T[i] = T[i];
+  correspond_kernel<<<nblk, kThreads, 0, ctx->stream>>>(tgt->grid, src->d_xyz, src->d_nrm_orig, n, X, dist * dist, normal_cos,
+                                                        d_match, d_counts);
+  scan_counts_kernel<<<1, 256, 0, ctx->stream>>>(d_counts, d_off, nblk);
+  compact_kernel<<<nblk, kThreads, 0, ctx->stream>>>(d_match, d_off, src->d_xyz, n, d_pairs, pcap, d_info);
+  ctx->launches += 3;
+  cudaError_t e = cudaGetLastError();
+  int total = 0;
+  double acc[13];
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&total, d_off + nblk, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && info36) e = cudaMemcpyAsync(acc, d_info, sizeof acc, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e == cudaSuccess && pcap && total > 0)
+    e = cudaMemcpy(pairs, d_pairs, sizeof(int32_t) * 2 * std::min((size_t)total, pcap), cudaMemcpyDeviceToHost);
+  cudaFree(d_match); cudaFree(d_counts); cudaFree(d_off); cudaFree(d_pairs); cudaFree(d_info);
+  if (e != cudaSuccess) { er::set_error("correspondences: %s", cudaGetErrorString(e)); return ER_ERR_CUDA; }
+  *n_out = (size_t)total;
+  if (info36) {
+    double* I = info36;
+    I[0] = I[7] = I[14] = acc[0];
+    I[0 * 6 + 4] = I[4 * 6 + 0] = acc[1];  I[0 * 6 + 5] = I[5 * 6 + 0] = acc[2];
+    I[1 * 6 + 3] = I[3 * 6 + 1] = acc[3];  I[1 * 6 + 5] = I[5 * 6 + 1] = acc[4];
+    I[2 * 6 + 3] = I[3 * 6 + 2] = acc[5];  I[2 * 6 + 4] = I[4 * 6 + 2] = acc[6];
+    I[3 * 6 + 3] = acc[7];  I[3 * 6 + 4] = I[4 * 6 + 3] = acc[8];  I[3 * 6 + 5] = I[5 * 6 + 3] = acc[9];
+    I[4 * 6 + 4] = acc[10]; I[4 * 6 + 5] = I[5 * 6 + 4] = acc[11];
+    I[5 * 6 + 5] = acc[12];
+  }
+  return ER_OK;
+}
+
+int er_icp_event_record(int device, int slot) {
+  IcpCtx* ctx = get_ctx(device);
+  ER_ARG(ctx && slot >= 0 && slot < kMaxEvents, "icp event: bad device or slot");
+  ER_CUDA(cudaSetDevice(device));
+  ER_CUDA(cudaEventRecord(ctx->events[slot], ctx->stream));
+  return ER_OK;
+}
+
+int er_icp_event_elapsed_ms(int device, int a, int b, float* ms) {
+  IcpCtx* ctx = get_ctx(device);
+  ER_ARG(ctx && ms && a >= 0 && a < kMaxEvents && b >= 0 && b < kMaxEvents, "icp event: bad device or slot");
+  ER_CUDA(cudaSetDevice(device));
+  ER_CUDA(cudaEventSynchronize(ctx->events[b]));
+  ER_CUDA(cudaEventElapsedTime(ms, ctx->events[a], ctx->events[b]));
+  return ER_OK;
+}
+
+uint64_t er_icp_launch_count(int device) {
+  IcpCtx* ctx = get_ctx(device);
+  return ctx ? ctx->launches : 0;
+}
+
+int er_icp_sync(int device) {
+  IcpCtx* ctx = get_ctx(device);
+  ER_ARG(ctx, "no CUDA context");
+  ER_CUDA(cudaSetDevice(device));
+  ER_CUDA(cudaStreamSynchronize(ctx->stream));
+  return ER_OK;
+}
+
+}  // extern "C"

@@ -59,6 +59,26 @@ def lib():
         L.oracle_reproject.argtypes = [C.c_void_p, u16p, dp, dp, dp, dp, fp, C.c_int, C.c_float]
         L.oracle_mat4_inverse.argtypes = [dp, dp]
         L.oracle_mat4_mul.argtypes = [dp, dp, dp]
+        i32p = C.POINTER(C.c_int32)
+        L.oracle_cloud_create.restype = C.c_void_p
+        L.oracle_cloud_create.argtypes = [fp, fp, C.c_int, C.c_double]
+        L.oracle_cloud_free.argtypes = [C.c_void_p]
+        L.oracle_nn_brute.restype = C.c_int
+        L.oracle_nn_brute.argtypes = [C.c_void_p, fp, fp]
+        L.oracle_nn_grid.restype = C.c_int
+        L.oracle_nn_grid.argtypes = [C.c_void_p, fp, fp]
+        L.oracle_icp_count_inliers.restype = C.c_int
+        L.oracle_icp_count_inliers.argtypes = [C.c_void_p, C.c_void_p, dp, C.c_double, C.c_int]
+        L.oracle_solve6.restype = C.c_int
+        L.oracle_solve6.argtypes = [dp, dp, dp]
+        L.oracle_icp_align.restype = C.c_int
+        L.oracle_icp_align.argtypes = [C.c_void_p, C.c_void_p, dp, C.c_double, C.c_int, C.c_double, C.c_int, dp, ip, dp,
+                                       C.c_int]
+        L.oracle_icp_align_batch.argtypes = [C.POINTER(C.c_void_p), ip, ip, C.c_int, dp, C.c_double, C.c_int, C.c_double,
+                                             C.c_int, dp, ip, dp, C.c_int]
+        L.oracle_icp_correspondences.restype = C.c_int
+        L.oracle_icp_correspondences.argtypes = [C.c_void_p, C.c_void_p, dp, C.c_double, C.c_double, i32p, C.c_int, dp,
+                                                 C.c_int]
         _lib = L
     return _lib
 
@@ -159,6 +179,89 @@ class OracleTSDF:
         if n:
             lib().oracle_tsdf_extract(self._h, _fp(out), n)
         return out
+
+
+class OracleCloud:
+    """One fragment for the ICP oracle (icp_oracle.c): xyz/normals float32 [n,3]; cell >= any search radius."""
+
+    def __init__(self, xyz, nrm, cell: float = 0.03):
+        self.xyz = np.ascontiguousarray(xyz, dtype=np.float32).reshape(-1, 3)
+        self.nrm = np.ascontiguousarray(nrm, dtype=np.float32).reshape(-1, 3)
+        self._h = C.c_void_p(lib().oracle_cloud_create(_fp(self.xyz), _fp(self.nrm), len(self.xyz), float(cell)))
+
+    def __len__(self):
+        return len(self.xyz)
+
+    def close(self):
+        if self._h:
+            lib().oracle_cloud_free(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def nn(self, q, brute=False):
+        q = np.ascontiguousarray(q, dtype=np.float32).reshape(3)
+        d2 = C.c_float()
+        fn = lib().oracle_nn_brute if brute else lib().oracle_nn_grid
+        return fn(self._h, _fp(q), C.byref(d2)), d2.value
+
+
+def icp_count_inliers(tgt: OracleCloud, src: OracleCloud, T, dist: float, threads: int = 8) -> int:
+    T = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+    return lib().oracle_icp_count_inliers(tgt._h, src._h, _dp(T), float(dist), threads)
+
+
+def icp_align(tgt: OracleCloud, src: OracleCloud, Tinit, max_dist=0.03, max_iter=20, eps=1e-6, fixed_iters=False,
+              threads: int = 8):
+    """Returns (T [4,4] float64, iterations, mean NN^2 of the last iteration, converged)."""
+    Tinit = np.ascontiguousarray(Tinit, dtype=np.float64).reshape(16)
+    out = np.empty(16, dtype=np.float64)
+    it = C.c_int()
+    fit = C.c_double()
+    conv = lib().oracle_icp_align(tgt._h, src._h, _dp(Tinit), float(max_dist), int(max_iter), float(eps),
+                                  int(bool(fixed_iters)), _dp(out), C.byref(it), C.byref(fit), threads)
+    return out.reshape(4, 4), it.value, fit.value, bool(conv)
+
+
+def icp_align_batch(clouds, tgt_idx, src_idx, Tinit, max_dist=0.03, max_iter=20, eps=1e-6, fixed_iters=False,
+                    threads: int = 8):
+    """Pair loop of CCorresApp::Registration (omp over pairs, `threads` threads, each pair single-threaded)."""
+    n = len(tgt_idx)
+    arr = (C.c_void_p * len(clouds))(*[c._h for c in clouds])
+    ti = np.ascontiguousarray(tgt_idx, dtype=np.int32)
+    si = np.ascontiguousarray(src_idx, dtype=np.int32)
+    Ti = np.ascontiguousarray(Tinit, dtype=np.float64).reshape(n, 16)
+    out = np.empty((n, 16), dtype=np.float64)
+    its = np.empty(n, dtype=np.int32)
+    fit = np.empty(n, dtype=np.float64)
+    lib().oracle_icp_align_batch(arr, ti.ctypes.data_as(C.POINTER(C.c_int)), si.ctypes.data_as(C.POINTER(C.c_int)), n,
+                                 _dp(Ti), float(max_dist), int(max_iter), float(eps), int(bool(fixed_iters)), _dp(out),
+                                 its.ctypes.data_as(C.POINTER(C.c_int)), _dp(fit), threads)
+    return out.reshape(n, 4, 4), its, fit
+
+
+def icp_correspondences(tgt: OracleCloud, src: OracleCloud, T, dist=0.015, normal_cos=0.8660, want_info=True,
+                        threads: int = 8):
+    """Returns (pairs int32 [m,2] = (target idx, source idx), info [6,6] or None)."""
+    T = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
+    pairs = np.empty((len(src), 2), dtype=np.int32)
+    info = np.zeros(36, dtype=np.float64) if want_info else None
+    m = lib().oracle_icp_correspondences(tgt._h, src._h, _dp(T), float(dist), float(normal_cos),
+                                         pairs.ctypes.data_as(C.POINTER(C.c_int32)), len(src),
+                                         _dp(info) if want_info else None, threads)
+    return pairs[:m].copy(), (info.reshape(6, 6) if want_info else None)
+
+
+def solve6(A, b):
+    A = np.ascontiguousarray(A, dtype=np.float64).reshape(36)
+    b = np.ascontiguousarray(b, dtype=np.float64).reshape(6)
+    x = np.empty(6, dtype=np.float64)
+    rc = lib().oracle_solve6(_dp(A), _dp(b), _dp(x))
+    return x if rc == 0 else None
 
 
 def sort_world(xyzi: np.ndarray) -> np.ndarray:

@@ -13,7 +13,7 @@ sys.path.insert(0, ROOT)
 from elasticreconstruction_b200 import capi, synth  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 30
-fusion = int(sys.argv[2]) if len(sys.argv) > 2 else 1
+fusion = int(sys.argv[2]) if len(sys.argv) > 2 else 32
 start = int(sys.argv[3]) if len(sys.argv) > 3 else 300
 poses = synth.quantize_log(synth.loop_trajectory(1000))[start:start + n]
 frames = synth.room_depth(poses)
