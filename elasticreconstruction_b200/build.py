@@ -89,6 +89,12 @@ def build_apps(force: bool = False, verbose: bool = False):
                 print(" ".join(cmd), flush=True)
             subprocess.check_call(cmd)
         outs.append(out)
+    tool_src = os.path.join(apps_dir, "er_io_tool.cpp")
+    if os.path.exists(tool_src):
+        out = os.path.join(BIN_DIR, "er_io_tool")
+        if force or _stale(out, [tool_src] + hdrs):
+            subprocess.check_call(["g++", "-O2", "-std=c++17", "-I", apps_dir, tool_src, "-o", out])
+        outs.append(out)
     return outs
 
 

@@ -216,6 +216,34 @@ def make_fragment(seed: int, n_target: int = 200_000, lo: float = 0.25, hi: floa
     return pts[keep].astype(np.float32), nrm[keep].astype(np.float32)
 
 
+def fragment_frame(i: int) -> np.ndarray:
+    """Local frame F_i of fragment i (local -> world): a small rigid motion about the room corner, so that every
+    fragment stays inside its own [0,3]^3 volume (FragmentOptimizer/PointCloud.h:107-110).  Fragment 0 is the world."""
+    if i == 0:
+        return np.eye(4)
+    rng = np.random.default_rng(SEED + 15485863 * i + 3)
+    R = rot_axis(rng.normal(size=3), math.radians(8.0) * rng.uniform(0.2, 1.0))
+    c = np.array([1.0, 1.0, 1.0])
+    t = rng.uniform(-0.08, 0.08, size=3)
+    return make_pose(R, c - R @ c + t)
+
+
+def make_local_fragment(i: int, n_target: int = 200_000):
+    """Fragment i expressed in its own frame: p_local = F_i^-1 p_world, normals rotated alike (float32)."""
+    xyz, nrm = make_fragment(i, n_target)
+    Finv = np.linalg.inv(fragment_frame(i))
+    xyz = (xyz.astype(np.float64) @ Finv[:3, :3].T + Finv[:3, 3]).astype(np.float32)
+    nrm = (nrm.astype(np.float64) @ Finv[:3, :3].T).astype(np.float32)
+    return xyz, nrm
+
+
+def pair_init(i: int, j: int, max_rot_deg: float = 1.5, max_trans: float = 0.015) -> np.ndarray:
+    """Initial transform of pair (target i, source j): true relative pose F_i^-1 F_j times a perturbation that
+    leaves nearest neighbours within reg_dist = 0.03 in the basin."""
+    T_true = np.linalg.inv(fragment_frame(i)) @ fragment_frame(j)
+    return T_true @ perturbation(1000 * i + j, max_rot_deg, max_trans)
+
+
 def perturbation(seed: int, max_rot_deg: float = 1.5, max_trans: float = 0.015) -> np.ndarray:
     rng = np.random.default_rng(SEED + 104729 * seed + 1)
     axis = rng.normal(size=3)

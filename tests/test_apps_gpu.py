@@ -1,0 +1,168 @@
+"""GPU tests of the two drop-in executables: same files in, same files out as the reference.
+
+Integrate is compared with the VERBATIM reference binary (oracle/_ref/Integrate_ref, which travels to the GPU box
+as a built file) on identical input files; BuildCorrespondence against a Python restatement of CCorresApp's control
+flow driven by the restated ICP oracle (PCL is not available, parity unpinned -- see oracle/icp_oracle.c)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+from elasticreconstruction_b200 import build, synth
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "elasticreconstruction_b200", "bin")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def apps():
+    build.build_library()
+    build.build_apps()
+
+
+def run(cmd, cwd):
+    p = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    return p.returncode, p.stdout
+
+
+@pytest.mark.parametrize("mk", helpers.ALL_SCENES, ids=lambda f: f.__name__)
+def test_integrate_cli_matches_reference_binary(oracle, tmp_path, mk):
+    sc = mk()
+    d = str(tmp_path)
+    args = helpers.write_scene(sc, d)
+    mine_pcd = os.path.join(d, "mine.pcd")
+    my_args = [a if a != os.path.join(d, "world.pcd") else mine_pcd for a in args]
+    rc, out = run([os.path.join(BIN, "Integrate")] + my_args, d)
+    assert rc == 0, out
+    mine = oracle.sort_world(synth.read_pcd_xyzi(mine_pcd))
+    if os.path.exists(oracle.REF_INTEGRATE):
+        ref_out, _ = oracle.run_reference_integrate(args, cwd=d)
+        ref = oracle.sort_world(synth.read_pcd_xyzi(os.path.join(d, "world.pcd")))
+        line = [l for l in ref_out.splitlines() if l.startswith("Total ")]
+        assert line and line[0] in out                      # "Total N frames processed."
+        assert ("%d voxel points have been written." % len(ref)) in out
+    else:
+        vol = oracle.OracleTSDF()
+        helpers.run_scene(vol, sc, mul=oracle.mat4_mul)
+        ref = oracle.sort_world(vol.extract())
+    assert mine.shape == ref.shape
+    assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32))
+
+
+def test_integrate_cli_help_and_bad_source(tmp_path):
+    rc, out = run([os.path.join(BIN, "Integrate")], str(tmp_path))
+    assert rc == 0 and "--ref_traj <log_file>" in out            # no arguments: help, rc 0 (Integrate.cpp:37-39)
+    rc, out = run([os.path.join(BIN, "Integrate"), "-oni", "missing.raw"], str(tmp_path))
+    assert rc != 0 and "Can't open depth source" in out          # Integrate.cpp:60
+
+
+def test_integrate_cli_start_end_window(oracle, tmp_path):
+    sc = helpers.scene_room(n=6)
+    d = str(tmp_path)
+    args = helpers.write_scene(sc, d) + ["--start_from", "2", "--end_at", "4"]
+    rc, out = run([os.path.join(BIN, "Integrate")] + args, d)
+    assert rc == 0 and "Total 5 frames processed." in out         # frame 5 > end_at sets exit (IntegrateApp.cpp:209-216)
+    vol = oracle.OracleTSDF()
+    helpers.run_app(vol, sc["frames"], sc["traj"], start_from=2, end_at=4)
+    ref = oracle.sort_world(vol.extract())
+    mine = oracle.sort_world(synth.read_pcd_xyzi(os.path.join(d, "world.pcd")))
+    assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32))
+
+
+# ------------------------------------------------------------------------------------------------ BuildCorrespondence
+def emulate_corres_app(oracle, clouds, pairs, Tinit, num, reg_dist=0.03, reg_ratio=0.25, reg_num=40000,
+                       dist_thresh=0.015, normal_thresh=0.8660, registration=True):
+    """CCorresApp::{Registration,FindCorrespondence} (CorresApp.cpp:112-319) on top of the oracle primitives."""
+    recs = []
+    for (i, j), T in zip(pairs, Tinit):
+        frame, T = num, np.array(T, dtype=np.float64)
+        if registration:
+            cnt = oracle.icp_count_inliers(clouds[i], clouds[j], T, reg_dist)
+            r1, r2 = cnt / len(clouds[i]), cnt / len(clouds[j])
+            if cnt >= reg_num or (r1 > reg_ratio and r2 > reg_ratio):
+                frame = cnt
+                T = oracle.icp_align(clouds[i], clouds[j], T, reg_dist, 20, 1e-6, False)[0]
+            else:
+                frame = -1
+        corr, info = None, None
+        if frame != -1:
+            corr, info = oracle.icp_correspondences(clouds[i], clouds[j], T, dist_thresh, normal_thresh)
+            if len(corr) / frame < 0.5:
+                frame = -1 if reg_num > 0 else len(corr)
+            else:
+                frame = len(corr)
+        recs.append(dict(i=i, j=j, frame=frame, T=T, corr=corr, info=info))
+    return recs
+
+
+def parse_log(path):
+    L = [l for l in open(path) if not l.startswith("#")]
+    out = []
+    for k in range(len(L) // 5):
+        ids = [int(x) for x in L[5 * k].split()]
+        T = np.array([[float(x) for x in L[5 * k + 1 + r].split()] for r in range(4)])
+        out.append((ids, T))
+    return out
+
+
+def test_buildcorrespondence_cli_matches_emulation(oracle, tmp_path):
+    d = str(tmp_path / "data")
+    os.makedirs(d)
+    n_frag = 4
+    frags = [synth.make_local_fragment(i, 30000) for i in range(n_frag)]
+    for i, (x, n) in enumerate(frags):
+        synth.write_pcd_xyzrgbnormal(os.path.join(d, "cloud_bin_%d.pcd" % i), x, n)
+    pairs = [(i, j) for i in range(n_frag) for j in range(i + 1, n_frag)]
+    Tinit = [synth.quantize_log(synth.pair_init(i, j)) for (i, j) in pairs]
+    Tinit[-1] = synth.quantize_log(Tinit[-1] @ synth.make_pose(np.eye(3), [2.0, 0, 0]))      # hopeless pair -> rejected
+    synth.write_log(os.path.join(d, "pairs.log"), np.array(Tinit), ids=[(i, j, n_frag) for (i, j) in pairs])
+    cwd = str(tmp_path / "run")
+    os.makedirs(cwd)
+    rc, out = run([os.path.join(BIN, "BuildCorrespondence"), "--reg_traj", os.path.join(d, "pairs.log"), "--registration",
+                   "--reg_num", "5000", "--output_information", "--save_xyzn"], cwd)
+    assert rc == 0, out
+    clouds = [oracle.OracleCloud(x, n, 0.03) for (x, n) in frags]
+    recs = emulate_corres_app(oracle, clouds, pairs, Tinit, n_frag, reg_num=5000)
+    got = parse_log(os.path.join(cwd, "reg_output.log"))           # written to the CWD (CorresApp.cpp:323)
+    assert len(got) == len(recs)
+    assert sum(r["frame"] == -1 for r in recs) >= 1 and sum(r["frame"] > 0 for r in recs) >= 4
+    info_lines = open(os.path.join(cwd, "reg_output.info")).read().split("\n")
+    for k, (r, (ids, T)) in enumerate(zip(recs, got)):
+        assert ids[:2] == [r["i"], r["j"]]
+        assert ids[2] == r["frame"], (ids, r["frame"])
+        assert np.linalg.norm(T - r["T"]) <= 1e-5 + 4e-8        # 1e-5 bar + the %.8f text rounding
+        fn = os.path.join(d, "corres_%d_%d.txt" % (r["i"], r["j"]))
+        if r["corr"] is not None:
+            mine = np.loadtxt(fn, dtype=np.int64).reshape(-1, 2)
+            # the correspondence set depends on the pose in the last float bits; require near-identity of the sets
+            a = set(map(tuple, mine.tolist())); b = set(map(tuple, r["corr"].tolist()))
+            assert len(a ^ b) <= max(4, len(b) // 2000), (len(a), len(b), len(a ^ b))
+            blk = np.array([[float(x) for x in info_lines[7 * k + 1 + q].split()] for q in range(6)])
+            assert abs(blk[0, 0] - len(mine)) < 0.5
+            assert np.allclose(blk, r["info"], rtol=2e-3, atol=1.0)
+        else:
+            assert not os.path.exists(fn)
+    x0 = np.loadtxt(os.path.join(d, "cloud_bin_xyzn_0.xyzn"))
+    assert x0.shape == (len(frags[0][0]), 6) and np.allclose(x0[:, :3], frags[0][0], atol=5e-7)
+
+
+def test_buildcorrespondence_traj_mode_creates_candidates(tmp_path):
+    """--traj/--num mode: candidate pairs from odometry + volume overlap (CorresApp.cpp:40-69)."""
+    d = str(tmp_path / "data")
+    os.makedirs(d)
+    n_frag, interval = 3, 2
+    for i in range(n_frag):
+        x, n = synth.make_local_fragment(i, 5000)
+        synth.write_pcd_xyzrgbnormal(os.path.join(d, "cloud_bin_%d.pcd" % i), x, n)
+    poses = [synth.make_pose(synth.rot_axis([0, 1, 0], 0.01 * k), [0.01 * k, 0, 0]) for k in range(n_frag * interval)]
+    synth.write_log(os.path.join(d, "traj.log"), synth.quantize_log(np.array(poses)))
+    cwd = str(tmp_path / "run")
+    os.makedirs(cwd)
+    rc, out = run([os.path.join(BIN, "BuildCorrespondence"), "--traj", os.path.join(d, "traj.log"), "--num", str(n_frag),
+                   "--interval", str(interval)], cwd)
+    assert rc == 0 and "3 initial matching candidates are created." in out, out
+    got = parse_log(os.path.join(cwd, "reg_output.log"))
+    assert [g[0][:2] for g in got] == [[0, 1], [0, 2], [1, 2]]
