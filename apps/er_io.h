@@ -241,7 +241,8 @@ inline bool load_pcd_xyzn(const std::string& filename, PointCloudXYZN& cloud) {
     char key[64] = {0};
     if (std::sscanf(line, "%63s", key) != 1) continue;
     std::vector<std::string> tok;
-    for (char* p = std::strtok(line, " \t\r\n"); p; p = std::strtok(nullptr, " \t\r\n")) tok.push_back(p);
+    char* save = nullptr;      // strtok_r: fragments are loaded from several threads at once
+    for (char* p = strtok_r(line, " \t\r\n", &save); p; p = strtok_r(nullptr, " \t\r\n", &save)) tok.push_back(p);
     const std::string k = tok[0];
     if (tok.size() < 2 && k != "DATA") continue;
     if (k == "FIELDS" || k == "COLUMNS") fields.assign(tok.begin() + 1, tok.end());
@@ -289,7 +290,8 @@ inline bool load_pcd_xyzn(const std::string& filename, PointCloudXYZN& cloud) {
     for (size_t i = 0; i < points && ok; i++) {
       if (!std::fgets(line, sizeof line, f)) { ok = false; break; }
       size_t c = 0;
-      for (char* p = std::strtok(line, " \t\r\n"); p; p = std::strtok(nullptr, " \t\r\n"), c++) {
+      char* save = nullptr;
+      for (char* p = strtok_r(line, " \t\r\n", &save); p; p = strtok_r(nullptr, " \t\r\n", &save), c++) {
         // columns follow FIELDS x COUNT
         size_t fi = 0, acc = 0;
         while (fi < nf && acc + counts[fi] <= c) { acc += counts[fi]; fi++; }
