@@ -5,7 +5,7 @@
 //   CCorresApp::FindCorrespondence BuildCorrespondence/CorresApp.cpp:112-210 (:145-161 search, :186-208 information)
 // and the PCL 1.7 pieces those lines instantiate (not in the reference tree; semantics as restated in
 // oracle/icp_oracle.c, which is the definition this file is tested against):
-//   pcl::KdTreeFLANN::{setInputCloud,nearestKSearch}      -> uniform grid over the target + 3x3x3 cell search
+//   pcl::KdTreeFLANN::{setInputCloud,nearestKSearch}      -> uniform grid over the target + pruned 5x5x5 cell search
 //   CorrespondenceEstimation::determineCorrespondences     -> icp_iter_kernel (search + gate)
 //   TransformationEstimationPointToPlaneLLS                -> icp_iter_kernel (rows, 6x6 normal equations, solve)
 //   IterativeClosestPoint::computeTransformation           -> one launch of icp_iter_kernel per iteration, no host sync
@@ -49,6 +49,8 @@ struct GridDev {
   const int* cell_start;  // ncell + 1
   float org[3];
   float inv_cell;
+  float cell;
+  int rings;              // search neighbourhood in cells: rings * cell >= the largest admissible radius
   int dim[3];
 };
 
@@ -65,27 +67,79 @@ struct PairState {
   unsigned ticket;
 };
 
-// exact 1-NN inside the 27 cells around q; returns sorted position or -1.  Distance = ((dx*dx + dy*dy) + dz*dz)
-// in float (flann::L2_Simple order); ties go to the smallest original index.
+// exact 1-NN among all target points within `rings` cells of q (rings * cell >= the search radius); returns the
+// sorted position or -1.  Distance = ((dx*dx + dy*dy) + dz*dz) in float (flann::L2_Simple order); ties go to the
+// smallest original index.  The query's own cell is scanned first; every other cell column is visited only if
+// its lower distance bound (computed from the query's position inside its cell, minus a slack that covers the
+// float rounding of the cell assignment) does not exceed the best distance so far -- so a converged pair scans
+// a handful of candidates instead of the full neighbourhood, with the same result as the exhaustive scan.
+__device__ __forceinline__ void nn_scan(const GridDev& g, int s0, int s1, float qx, float qy, float qz, float& bd, int& best,
+                                        int& best_idx) {
+  for (int s = s0; s < s1; s++) {
+    const float4 p = __ldg(&g.pts[s]);
+    const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    const int idx = __float_as_int(p.w);
+    if (d2 < bd || (d2 == bd && idx < best_idx)) { bd = d2; best = s; best_idx = idx; }
+  }
+}
+
 __device__ __forceinline__ int nn_search(const GridDev& g, float qx, float qy, float qz, float& best_d2) {
-  const int cx = (int)floorf(__fmul_rn(__fsub_rn(qx, g.org[0]), g.inv_cell));
-  const int cy = (int)floorf(__fmul_rn(__fsub_rn(qy, g.org[1]), g.inv_cell));
-  const int cz = (int)floorf(__fmul_rn(__fsub_rn(qz, g.org[2]), g.inv_cell));
+  const float lx = __fmul_rn(__fsub_rn(qx, g.org[0]), g.inv_cell);
+  const float ly = __fmul_rn(__fsub_rn(qy, g.org[1]), g.inv_cell);
+  const float lz = __fmul_rn(__fsub_rn(qz, g.org[2]), g.inv_cell);
+  const float flx = floorf(lx), fly = floorf(ly), flz = floorf(lz);
   int best = -1, best_idx = 0x7fffffff;
   float bd = FLT_MAX;
-  const int z0 = max(cz - 1, 0), z1 = min(cz + 1, g.dim[2] - 1);
-  if (z0 <= z1) {
-    for (int ix = max(cx - 1, 0); ix <= min(cx + 1, g.dim[0] - 1); ix++) {
-      for (int iy = max(cy - 1, 0); iy <= min(cy + 1, g.dim[1] - 1); iy++) {
-        const int row = (ix * g.dim[1] + iy) * g.dim[2];
-        const int s0 = __ldg(&g.cell_start[row + z0]), s1 = __ldg(&g.cell_start[row + z1 + 1]);   // z cells are contiguous
-        for (int s = s0; s < s1; s++) {
-          const float4 p = __ldg(&g.pts[s]);
-          const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
-          const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-          const int idx = __float_as_int(p.w);
-          if (d2 < bd || (d2 == bd && idx < best_idx)) { bd = d2; best = s; best_idx = idx; }
-        }
+  const int K = g.rings;
+  // queries far outside the grid cannot have a neighbour within the radius
+  if (!(flx >= -(float)(K + 1) && flx <= (float)(g.dim[0] + K) && fly >= -(float)(K + 1) && fly <= (float)(g.dim[1] + K) &&
+        flz >= -(float)(K + 1) && flz <= (float)(g.dim[2] + K))) {
+    best_d2 = bd;
+    return -1;
+  }
+  const int cx = (int)flx, cy = (int)fly, cz = (int)flz;
+  const float fx = lx - flx, fy = ly - fly, fz = lz - flz;        // position inside the cell, [0, 1)
+  const float cell = g.cell, slack = 1e-5f * g.cell;
+  if (cx >= 0 && cx < g.dim[0] && cy >= 0 && cy < g.dim[1] && cz >= 0 && cz < g.dim[2]) {
+    const int c = (cx * g.dim[1] + cy) * g.dim[2] + cz;
+    nn_scan(g, __ldg(&g.cell_start[c]), __ldg(&g.cell_start[c + 1]), qx, qy, qz, bd, best, best_idx);
+  }
+  for (int ox = -K; ox <= K; ox++) {
+    const int ix = cx + ox;
+    if (ix < 0 || ix >= g.dim[0]) continue;
+    const float ax = fmaxf(0.0f, (ox > 0 ? ((float)ox - fx) : (ox < 0 ? (fx - (float)(ox + 1)) : 0.0f)) * cell - slack);
+    const float ax2 = ax * ax;
+    if (ax2 > bd) continue;
+    for (int oy = -K; oy <= K; oy++) {
+      const int iy = cy + oy;
+      if (iy < 0 || iy >= g.dim[1]) continue;
+      const float ay = fmaxf(0.0f, (oy > 0 ? ((float)oy - fy) : (oy < 0 ? (fy - (float)(oy + 1)) : 0.0f)) * cell - slack);
+      const float axy2 = ax2 + ay * ay;
+      if (axy2 > bd) continue;
+      // z cells of one (x, y) column are contiguous in memory: shrink the range to the cells that can still matter
+      int z1 = cz;                                                   // highest / lowest z cell still within reach
+      for (int oz = 1; oz <= K; oz++) {
+        const float az = fmaxf(0.0f, ((float)oz - fz) * cell - slack);
+        if (axy2 + az * az > bd) break;
+        z1 = cz + oz;
+      }
+      int zlo = cz;
+      for (int oz = 1; oz <= K; oz++) {
+        const float az = fmaxf(0.0f, (fz + (float)(oz - 1)) * cell - slack);
+        if (axy2 + az * az > bd) break;
+        zlo = cz - oz;
+      }
+      const int row = (ix * g.dim[1] + iy) * g.dim[2];
+      if (ox == 0 && oy == 0) {
+        // two separate runs around the already scanned centre cell
+        const int a0 = max(zlo, 0), a1 = min(cz - 1, g.dim[2] - 1);
+        if (a0 <= a1) nn_scan(g, __ldg(&g.cell_start[row + a0]), __ldg(&g.cell_start[row + a1 + 1]), qx, qy, qz, bd, best, best_idx);
+        const int b0 = max(cz + 1, 0), b1 = min(z1, g.dim[2] - 1);
+        if (b0 <= b1) nn_scan(g, __ldg(&g.cell_start[row + b0]), __ldg(&g.cell_start[row + b1 + 1]), qx, qy, qz, bd, best, best_idx);
+      } else {
+        const int a0 = max(zlo, 0), a1 = min(max(z1, cz), g.dim[2] - 1);
+        if (a0 <= a1) nn_scan(g, __ldg(&g.cell_start[row + a0]), __ldg(&g.cell_start[row + a1 + 1]), qx, qy, qz, bd, best, best_idx);
       }
     }
   }
@@ -138,48 +192,62 @@ __global__ void __launch_bounds__(kThreads) icp_iter_kernel(PairState* states, d
 #pragma unroll
   for (int i = 0; i < 12; i++) M[i] = S.Tinc[i];
   const GridDev g = S.tgt;
+
+  const int base = blockIdx.x * kPtsPerCta;
+  // phase 1: move the points and search (the double accumulators are not live yet: lower register pressure)
+  int match[kPtsPerThread];
+  float md2[kPtsPerThread];
+#pragma unroll
+  for (int it = 0; it < kPtsPerThread; it++) {
+    const int k = base + it * kThreads + tid;
+    match[it] = -1;
+    md2[it] = 0.0f;
+    if (k < S.n_src) {
+      float* cp = S.cur + 3 * (size_t)k;
+      const float x = cp[0], y = cp[1], z = cp[2];
+      // Matrix4f * (x, y, z, 1): ((m0*x + m1*y) + m2*z) + m3*1
+      const float sx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[0], x), __fmul_rn(M[1], y)), __fmul_rn(M[2], z)), M[3]);
+      const float sy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[4], x), __fmul_rn(M[5], y)), __fmul_rn(M[6], z)), M[7]);
+      const float sz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[8], x), __fmul_rn(M[9], y)), __fmul_rn(M[10], z)), M[11]);
+      cp[0] = sx; cp[1] = sy; cp[2] = sz;
+      float d2;
+      const int m = nn_search(g, sx, sy, sz, d2);
+      if (m >= 0 && !((double)d2 > max_d2)) { match[it] = m; md2[it] = d2; }
+    }
+  }
+  // phase 2: point-to-plane rows of the accepted correspondences
   double acc[kAcc];
 #pragma unroll
   for (int i = 0; i < kAcc; i++) acc[i] = 0.0;
-
-  const int base = blockIdx.x * kPtsPerCta;
 #pragma unroll 1
   for (int it = 0; it < kPtsPerThread; it++) {
+    const int m = match[it];
+    if (m < 0) continue;
     const int k = base + it * kThreads + tid;
-    if (k >= S.n_src) break;
-    float* cp = S.cur + 3 * (size_t)k;
-    const float x = cp[0], y = cp[1], z = cp[2];
-    // Matrix4f * (x, y, z, 1): ((m0*x + m1*y) + m2*z) + m3*1
-    const float sx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[0], x), __fmul_rn(M[1], y)), __fmul_rn(M[2], z)), M[3]);
-    const float sy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[4], x), __fmul_rn(M[5], y)), __fmul_rn(M[6], z)), M[7]);
-    const float sz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[8], x), __fmul_rn(M[9], y)), __fmul_rn(M[10], z)), M[11]);
-    cp[0] = sx; cp[1] = sy; cp[2] = sz;
-    float d2;
-    const int m = nn_search(g, sx, sy, sz, d2);
-    if (m >= 0 && !((double)d2 > max_d2)) {
-      const float4 t = __ldg(&g.pts[m]);
-      const float4 nn = __ldg(&g.nrm[m]);
-      const float dx = t.x, dy = t.y, dz = t.z, nx = nn.x, ny = nn.y, nz = nn.z;
-      acc[27] += (double)d2;
-      acc[28] += 1.0;
-      if (isfinite(sx) && isfinite(sy) && isfinite(sz) && isfinite(dx) && isfinite(dy) && isfinite(dz) && isfinite(nx) &&
-          isfinite(ny) && isfinite(nz)) {
-        // float expressions widened afterwards, as in PCL's estimateRigidTransformation (float operands)
-        const double a = (double)__fsub_rn(__fmul_rn(nz, sy), __fmul_rn(ny, sz));
-        const double b = (double)__fsub_rn(__fmul_rn(nx, sz), __fmul_rn(nz, sx));
-        const double c = (double)__fsub_rn(__fmul_rn(ny, sx), __fmul_rn(nx, sy));
-        float df = __fadd_rn(__fadd_rn(__fmul_rn(nx, dx), __fmul_rn(ny, dy)), __fmul_rn(nz, dz));
-        df = __fsub_rn(__fsub_rn(__fsub_rn(df, __fmul_rn(nx, sx)), __fmul_rn(ny, sy)), __fmul_rn(nz, sz));
-        const double d = (double)df;
-        const double dnx = (double)nx, dny = (double)ny, dnz = (double)nz;
-        acc[0] += a * a;   acc[1] += a * b;   acc[2] += a * c;   acc[3] += a * dnx;  acc[4] += a * dny;  acc[5] += a * dnz;
-        acc[6] += b * b;   acc[7] += b * c;   acc[8] += b * dnx; acc[9] += b * dny;  acc[10] += b * dnz;
-        acc[11] += c * c;  acc[12] += c * dnx; acc[13] += c * dny; acc[14] += c * dnz;
-        acc[15] += (double)__fmul_rn(nx, nx); acc[16] += (double)__fmul_rn(nx, ny); acc[17] += (double)__fmul_rn(nx, nz);
-        acc[18] += (double)__fmul_rn(ny, ny); acc[19] += (double)__fmul_rn(ny, nz);
-        acc[20] += (double)__fmul_rn(nz, nz);
-        acc[21] += a * d;  acc[22] += b * d;  acc[23] += c * d;  acc[24] += dnx * d;  acc[25] += dny * d;  acc[26] += dnz * d;
-      }
+    const float* cp = S.cur + 3 * (size_t)k;
+    const float sx = cp[0], sy = cp[1], sz = cp[2];
+    const float4 t = __ldg(&g.pts[m]);
+    const float4 nn = __ldg(&g.nrm[m]);
+    const float dx = t.x, dy = t.y, dz = t.z, nx = nn.x, ny = nn.y, nz = nn.z;
+    acc[27] += (double)md2[it];
+    acc[28] += 1.0;
+    if (isfinite(sx) && isfinite(sy) && isfinite(sz) && isfinite(dx) && isfinite(dy) && isfinite(dz) && isfinite(nx) &&
+        isfinite(ny) && isfinite(nz)) {
+      // float expressions widened afterwards, as in PCL's estimateRigidTransformation (float operands)
+      const double a = (double)__fsub_rn(__fmul_rn(nz, sy), __fmul_rn(ny, sz));
+      const double b = (double)__fsub_rn(__fmul_rn(nx, sz), __fmul_rn(nz, sx));
+      const double c = (double)__fsub_rn(__fmul_rn(ny, sx), __fmul_rn(nx, sy));
+      float df = __fadd_rn(__fadd_rn(__fmul_rn(nx, dx), __fmul_rn(ny, dy)), __fmul_rn(nz, dz));
+      df = __fsub_rn(__fsub_rn(__fsub_rn(df, __fmul_rn(nx, sx)), __fmul_rn(ny, sy)), __fmul_rn(nz, sz));
+      const double d = (double)df;
+      const double dnx = (double)nx, dny = (double)ny, dnz = (double)nz;
+      acc[0] += a * a;   acc[1] += a * b;   acc[2] += a * c;   acc[3] += a * dnx;  acc[4] += a * dny;  acc[5] += a * dnz;
+      acc[6] += b * b;   acc[7] += b * c;   acc[8] += b * dnx; acc[9] += b * dny;  acc[10] += b * dnz;
+      acc[11] += c * c;  acc[12] += c * dnx; acc[13] += c * dny; acc[14] += c * dnz;
+      acc[15] += (double)__fmul_rn(nx, nx); acc[16] += (double)__fmul_rn(nx, ny); acc[17] += (double)__fmul_rn(nx, nz);
+      acc[18] += (double)__fmul_rn(ny, ny); acc[19] += (double)__fmul_rn(ny, nz);
+      acc[20] += (double)__fmul_rn(nz, nz);
+      acc[21] += a * d;  acc[22] += b * d;  acc[23] += c * d;  acc[24] += dnx * d;  acc[25] += dny * d;  acc[26] += dnz * d;
     }
   }
   // ---- CTA reduction (fixed tree)
@@ -465,17 +533,21 @@ er_cloud* er_cloud_upload(int device, const float* xyz, const float* normals, si
       if (v > hi[a]) hi[a] = v;
     }
   if (n == 0) for (int a = 0; a < 3; a++) lo[a] = hi[a] = 0.f;
-  double cell = cell_size * 1.001;     // strictly larger than any admissible radius: neighbours differ by <= 1 cell
+  // cells of half the admissible radius (a hair more), searched two rings deep: fewer candidates per cell
+  int rings = 2;
+  double cell = cell_size * 1.001 / rings;
   int dim[3];
   for (;;) {
     double cells = 1;
     for (int a = 0; a < 3; a++) { dim[a] = (int)std::floor((hi[a] - lo[a]) / cell) + 1; cells *= dim[a]; }
     if (cells <= 64e6) break;
-    cell *= 2;
+    if (rings > 1) { rings--; cell = cell_size * 1.001 / rings; } else cell *= 2;
   }
-  c->cell = cell;
+  c->cell = cell * rings;               // the radius this grid supports
   GridDev& g = c->grid;
   g.inv_cell = (float)(1.0 / cell);
+  g.cell = (float)cell;
+  g.rings = rings;
   for (int a = 0; a < 3; a++) { g.org[a] = lo[a]; g.dim[a] = dim[a]; }
   const size_t ncell = (size_t)dim[0] * dim[1] * dim[2];
   std::vector<int> cell_start(ncell + 1, 0), cid(n);
