@@ -44,6 +44,16 @@ BYTES_PER_FRAME = W * H * 2
 
 
 # --------------------------------------------------------------------------------------------- helpers
+def load_traffic(kernel: str):
+    """DRAM bytes per launch of `kernel` from the committed ncu capture (profiles/traffic.json), or None."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(p))[kernel]
+        return t["dram_bytes_per_launch"] / t.get("units_per_launch", 1.0)
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -310,7 +320,8 @@ def main():
     peak, peak_src = load_peaks()
     achieved = alg_bytes_per_launch / int_s_per_launch / 1e9
     roofline = {"bound": "hbm", "kernel": "integrate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": None,
+                "frac": achieved / peak, "peak_source": peak_src, "traffic": load_traffic("integrate_kernel"),
+                "traffic_source": "ncu --set full capture of one 32-frame launch (profiles/traffic.json)",
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch, "us_per_launch": int_s_per_launch * 1e6,
                 "frames_per_launch": n_prof / n_launch,
                 "note": "algorithmic bytes = 16 B x updated voxels + 2 B x W x H per frame (SURVEY 8d); one launch "

@@ -105,42 +105,37 @@ __device__ __forceinline__ int nn_search(const GridDev& g, float qx, float qy, f
     const int c = (cx * g.dim[1] + cy) * g.dim[2] + cz;
     nn_scan(g, __ldg(&g.cell_start[c]), __ldg(&g.cell_start[c + 1]), qx, qy, qz, bd, best, best_idx);
   }
-  for (int ox = -K; ox <= K; ox++) {
-    const int ix = cx + ox;
-    if (ix < 0 || ix >= g.dim[0]) continue;
+  // one flat loop over the (2K+1)^2 cell columns (same trip count for every lane; the bound test is arithmetic only)
+  const int W = 2 * K + 1;
+  for (int col = 0; col < W * W; col++) {
+    const int ox = col / W - K, oy = col % W - K;
+    const int ix = cx + ox, iy = cy + oy;
     const float ax = fmaxf(0.0f, (ox > 0 ? ((float)ox - fx) : (ox < 0 ? (fx - (float)(ox + 1)) : 0.0f)) * cell - slack);
-    const float ax2 = ax * ax;
-    if (ax2 > bd) continue;
-    for (int oy = -K; oy <= K; oy++) {
-      const int iy = cy + oy;
-      if (iy < 0 || iy >= g.dim[1]) continue;
-      const float ay = fmaxf(0.0f, (oy > 0 ? ((float)oy - fy) : (oy < 0 ? (fy - (float)(oy + 1)) : 0.0f)) * cell - slack);
-      const float axy2 = ax2 + ay * ay;
-      if (axy2 > bd) continue;
-      // z cells of one (x, y) column are contiguous in memory: shrink the range to the cells that can still matter
-      int z1 = cz;                                                   // highest / lowest z cell still within reach
-      for (int oz = 1; oz <= K; oz++) {
-        const float az = fmaxf(0.0f, ((float)oz - fz) * cell - slack);
-        if (axy2 + az * az > bd) break;
-        z1 = cz + oz;
-      }
-      int zlo = cz;
-      for (int oz = 1; oz <= K; oz++) {
-        const float az = fmaxf(0.0f, (fz + (float)(oz - 1)) * cell - slack);
-        if (axy2 + az * az > bd) break;
-        zlo = cz - oz;
-      }
-      const int row = (ix * g.dim[1] + iy) * g.dim[2];
-      if (ox == 0 && oy == 0) {
-        // two separate runs around the already scanned centre cell
-        const int a0 = max(zlo, 0), a1 = min(cz - 1, g.dim[2] - 1);
-        if (a0 <= a1) nn_scan(g, __ldg(&g.cell_start[row + a0]), __ldg(&g.cell_start[row + a1 + 1]), qx, qy, qz, bd, best, best_idx);
-        const int b0 = max(cz + 1, 0), b1 = min(z1, g.dim[2] - 1);
-        if (b0 <= b1) nn_scan(g, __ldg(&g.cell_start[row + b0]), __ldg(&g.cell_start[row + b1 + 1]), qx, qy, qz, bd, best, best_idx);
-      } else {
-        const int a0 = max(zlo, 0), a1 = min(max(z1, cz), g.dim[2] - 1);
-        if (a0 <= a1) nn_scan(g, __ldg(&g.cell_start[row + a0]), __ldg(&g.cell_start[row + a1 + 1]), qx, qy, qz, bd, best, best_idx);
-      }
+    const float ay = fmaxf(0.0f, (oy > 0 ? ((float)oy - fy) : (oy < 0 ? (fy - (float)(oy + 1)) : 0.0f)) * cell - slack);
+    const float axy2 = ax * ax + ay * ay;
+    if (axy2 > bd || ix < 0 || ix >= g.dim[0] || iy < 0 || iy >= g.dim[1]) continue;
+    // z cells of one (x, y) column are contiguous in memory: shrink the range to the cells that can still matter
+    int zhi = cz, zlo = cz;
+    for (int oz = 1; oz <= K; oz++) {
+      const float az = fmaxf(0.0f, ((float)oz - fz) * cell - slack);
+      if (axy2 + az * az > bd) break;
+      zhi = cz + oz;
+    }
+    for (int oz = 1; oz <= K; oz++) {
+      const float az = fmaxf(0.0f, (fz + (float)(oz - 1)) * cell - slack);
+      if (axy2 + az * az > bd) break;
+      zlo = cz - oz;
+    }
+    const int row = (ix * g.dim[1] + iy) * g.dim[2];
+    if (ox == 0 && oy == 0) {
+      // two separate runs around the already scanned centre cell
+      const int a0 = max(zlo, 0), a1 = min(cz - 1, g.dim[2] - 1);
+      if (a0 <= a1) nn_scan(g, __ldg(&g.cell_start[row + a0]), __ldg(&g.cell_start[row + a1 + 1]), qx, qy, qz, bd, best, best_idx);
+      const int b0 = max(cz + 1, 0), b1 = min(zhi, g.dim[2] - 1);
+      if (b0 <= b1) nn_scan(g, __ldg(&g.cell_start[row + b0]), __ldg(&g.cell_start[row + b1 + 1]), qx, qy, qz, bd, best, best_idx);
+    } else {
+      const int a0 = max(zlo, 0), a1 = min(zhi, g.dim[2] - 1);
+      if (a0 <= a1) nn_scan(g, __ldg(&g.cell_start[row + a0]), __ldg(&g.cell_start[row + a1 + 1]), qx, qy, qz, bd, best, best_idx);
     }
   }
   best_d2 = bd;
@@ -181,7 +176,7 @@ __device__ bool solve6(double* A, double* b, double* x) {
 //   4. CTA partial -> global; the pair's last CTA sums the partials in index order, solves the 6x6 system,
 //      builds T_inc = Rz Ry Rx + t, updates final = T_inc * final and evaluates the convergence criteria.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads) icp_iter_kernel(PairState* states, double max_d2, int max_iter, double eps,
+__global__ void __launch_bounds__(kThreads, 3) icp_iter_kernel(PairState* states, double max_d2, int max_iter, double eps,
                                                             int fixed_iters) {
   PairState& S = states[blockIdx.y];
   if (blockIdx.x >= S.nblocks || S.done) return;
@@ -195,13 +190,13 @@ __global__ void __launch_bounds__(kThreads) icp_iter_kernel(PairState* states, d
 
   const int base = blockIdx.x * kPtsPerCta;
   // phase 1: move the points and search (the double accumulators are not live yet: lower register pressure)
-  int match[kPtsPerThread];
-  float md2[kPtsPerThread];
-#pragma unroll
+  __shared__ int s_match[kPtsPerThread][kThreads];
+  __shared__ float s_md2[kPtsPerThread][kThreads];
+#pragma unroll 1
   for (int it = 0; it < kPtsPerThread; it++) {
     const int k = base + it * kThreads + tid;
-    match[it] = -1;
-    md2[it] = 0.0f;
+    s_match[it][tid] = -1;
+    s_md2[it][tid] = 0.0f;
     if (k < S.n_src) {
       float* cp = S.cur + 3 * (size_t)k;
       const float x = cp[0], y = cp[1], z = cp[2];
@@ -212,7 +207,7 @@ __global__ void __launch_bounds__(kThreads) icp_iter_kernel(PairState* states, d
       cp[0] = sx; cp[1] = sy; cp[2] = sz;
       float d2;
       const int m = nn_search(g, sx, sy, sz, d2);
-      if (m >= 0 && !((double)d2 > max_d2)) { match[it] = m; md2[it] = d2; }
+      if (m >= 0 && !((double)d2 > max_d2)) { s_match[it][tid] = m; s_md2[it][tid] = d2; }
     }
   }
   // phase 2: point-to-plane rows of the accepted correspondences
@@ -221,7 +216,7 @@ __global__ void __launch_bounds__(kThreads) icp_iter_kernel(PairState* states, d
   for (int i = 0; i < kAcc; i++) acc[i] = 0.0;
 #pragma unroll 1
   for (int it = 0; it < kPtsPerThread; it++) {
-    const int m = match[it];
+    const int m = s_match[it][tid];
     if (m < 0) continue;
     const int k = base + it * kThreads + tid;
     const float* cp = S.cur + 3 * (size_t)k;
@@ -229,7 +224,7 @@ __global__ void __launch_bounds__(kThreads) icp_iter_kernel(PairState* states, d
     const float4 t = __ldg(&g.pts[m]);
     const float4 nn = __ldg(&g.nrm[m]);
     const float dx = t.x, dy = t.y, dz = t.z, nx = nn.x, ny = nn.y, nz = nn.z;
-    acc[27] += (double)md2[it];
+    acc[27] += (double)s_md2[it][tid];
     acc[28] += 1.0;
     if (isfinite(sx) && isfinite(sy) && isfinite(sz) && isfinite(dx) && isfinite(dy) && isfinite(dz) && isfinite(nx) &&
         isfinite(ny) && isfinite(nz)) {

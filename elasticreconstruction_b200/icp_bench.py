@@ -27,6 +27,16 @@ def all_pairs(n):
     return [(i, j) for i in range(n) for j in range(i + 1, n)]
 
 
+def _traffic_per_pair_iteration():
+    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+    try:
+        import json
+        t = json.load(open(p))["icp_iter_kernel"]
+        return t["dram_bytes_per_launch"] / t.get("units_per_launch", 1.0)
+    except Exception:
+        return None
+
+
 def run(local: int, rank: int, world: int, barrier, peak_gbs: float = 0.0, cpu_pairs: int = 8,
         num_fragments: int = NUM_FRAGMENTS, points: int = POINTS, warmup_pairs: int = 32):
     import torch
@@ -85,7 +95,7 @@ def run(local: int, rank: int, world: int, barrier, peak_gbs: float = 0.0, cpu_p
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(len(mine) * 136),
                 "note": "includes fragment upload and host-side grid build for all %d fragments" % num_fragments},
         "roofline": {"bound": "hbm", "kernel": "icp_iter_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
-                     "frac": (achieved / peak_gbs) if peak_gbs else None, "traffic": None,
+                     "frac": (achieved / peak_gbs) if peak_gbs else None, "traffic": _traffic_per_pair_iteration(),
                      "algorithmic_bytes_per_pair_iteration": alg_bytes,
                      "note": "one pair's working set (~7 MB) sits in L2: the search is latency/L2-bound by construction "
                              "(SURVEY 8d); frac vs HBM peak is reported because the metric asks for it"},
