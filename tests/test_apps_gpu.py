@@ -24,7 +24,7 @@ def apps():
 
 
 def run(cmd, cwd):
-    p = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    p = subprocess.run(cmd, cwd=cwd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=180)
     return p.returncode, p.stdout
 
 
