@@ -329,6 +329,8 @@ def main():
                 "touch_us_per_frame": t_touch * 1e3 / n_prof, "classify_us_per_frame": t_cls * 1e3 / n_prof,
                 "integrate_us_per_frame": t_int * 1e3 / n_prof,
                 "updated_voxels_per_frame": upd / n_prof, "active_blocks_per_frame": blocks / n_prof,
+                "one_voxels_per_frame": 64.0 * (st1["one_pairs"] - st0["one_pairs"]) / n_prof,
+                "full_voxels_per_frame": 64.0 * (st1["full_pairs"] - st0["full_pairs"]) / n_prof,
                 "dense_bytes_per_frame": 16.0 * 262144 * blocks / n_prof + 2.0 * W * H}
     del vol2
 

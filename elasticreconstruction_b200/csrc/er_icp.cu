@@ -37,8 +37,8 @@
 
 namespace {
 
-constexpr int kThreads = 256;
-constexpr int kPtsPerThread = 4;
+constexpr int kThreads = 128;
+constexpr int kPtsPerThread = 8;
 constexpr int kPtsPerCta = kThreads * kPtsPerThread;
 constexpr int kAcc = 29;               // 21 (upper ATA) + 6 (ATb) + sum d^2 + count
 constexpr int kMaxEvents = 16;
@@ -105,37 +105,45 @@ __device__ __forceinline__ int nn_search(const GridDev& g, float qx, float qy, f
     const int c = (cx * g.dim[1] + cy) * g.dim[2] + cz;
     nn_scan(g, __ldg(&g.cell_start[c]), __ldg(&g.cell_start[c + 1]), qx, qy, qz, bd, best, best_idx);
   }
-  // one flat loop over the (2K+1)^2 cell columns (same trip count for every lane; the bound test is arithmetic only)
-  const int W = 2 * K + 1;
-  for (int col = 0; col < W * W; col++) {
-    const int ox = col / W - K, oy = col % W - K;
-    const int ix = cx + ox, iy = cy + oy;
+  // per axis, the cell offsets whose slab can still hold something closer than the best so far (after the centre
+  // cell that is usually just {0} or {0, +-1}); an empty centre cell leaves bd = FLT_MAX and hence the full range
+  int xlo = 0, xhi = 0, ylo = 0, yhi = 0;
+  for (int o = 1; o <= K; o++) { const float a = fmaxf(0.0f, ((float)o - fx) * cell - slack); if (a * a > bd) break; xhi = o; }
+  for (int o = 1; o <= K; o++) { const float a = fmaxf(0.0f, (fx + (float)(o - 1)) * cell - slack); if (a * a > bd) break; xlo = -o; }
+  for (int o = 1; o <= K; o++) { const float a = fmaxf(0.0f, ((float)o - fy) * cell - slack); if (a * a > bd) break; yhi = o; }
+  for (int o = 1; o <= K; o++) { const float a = fmaxf(0.0f, (fy + (float)(o - 1)) * cell - slack); if (a * a > bd) break; ylo = -o; }
+  for (int ox = xlo; ox <= xhi; ox++) {
+    const int ix = cx + ox;
+    if (ix < 0 || ix >= g.dim[0]) continue;
     const float ax = fmaxf(0.0f, (ox > 0 ? ((float)ox - fx) : (ox < 0 ? (fx - (float)(ox + 1)) : 0.0f)) * cell - slack);
-    const float ay = fmaxf(0.0f, (oy > 0 ? ((float)oy - fy) : (oy < 0 ? (fy - (float)(oy + 1)) : 0.0f)) * cell - slack);
-    const float axy2 = ax * ax + ay * ay;
-    if (axy2 > bd || ix < 0 || ix >= g.dim[0] || iy < 0 || iy >= g.dim[1]) continue;
-    // z cells of one (x, y) column are contiguous in memory: shrink the range to the cells that can still matter
-    int zhi = cz, zlo = cz;
-    for (int oz = 1; oz <= K; oz++) {
-      const float az = fmaxf(0.0f, ((float)oz - fz) * cell - slack);
-      if (axy2 + az * az > bd) break;
-      zhi = cz + oz;
-    }
-    for (int oz = 1; oz <= K; oz++) {
-      const float az = fmaxf(0.0f, (fz + (float)(oz - 1)) * cell - slack);
-      if (axy2 + az * az > bd) break;
-      zlo = cz - oz;
-    }
-    const int row = (ix * g.dim[1] + iy) * g.dim[2];
-    if (ox == 0 && oy == 0) {
-      // two separate runs around the already scanned centre cell
-      const int a0 = max(zlo, 0), a1 = min(cz - 1, g.dim[2] - 1);
-      if (a0 <= a1) nn_scan(g, __ldg(&g.cell_start[row + a0]), __ldg(&g.cell_start[row + a1 + 1]), qx, qy, qz, bd, best, best_idx);
-      const int b0 = max(cz + 1, 0), b1 = min(zhi, g.dim[2] - 1);
-      if (b0 <= b1) nn_scan(g, __ldg(&g.cell_start[row + b0]), __ldg(&g.cell_start[row + b1 + 1]), qx, qy, qz, bd, best, best_idx);
-    } else {
-      const int a0 = max(zlo, 0), a1 = min(zhi, g.dim[2] - 1);
-      if (a0 <= a1) nn_scan(g, __ldg(&g.cell_start[row + a0]), __ldg(&g.cell_start[row + a1 + 1]), qx, qy, qz, bd, best, best_idx);
+    for (int oy = ylo; oy <= yhi; oy++) {
+      const int iy = cy + oy;
+      const float ay = fmaxf(0.0f, (oy > 0 ? ((float)oy - fy) : (oy < 0 ? (fy - (float)(oy + 1)) : 0.0f)) * cell - slack);
+      const float axy2 = ax * ax + ay * ay;
+      if (axy2 > bd || iy < 0 || iy >= g.dim[1]) continue;
+      // z cells of one (x, y) column are contiguous in memory: shrink the range to the cells that can still matter
+      int zhi = cz, zlo = cz;
+      for (int oz = 1; oz <= K; oz++) {
+        const float az = fmaxf(0.0f, ((float)oz - fz) * cell - slack);
+        if (axy2 + az * az > bd) break;
+        zhi = cz + oz;
+      }
+      for (int oz = 1; oz <= K; oz++) {
+        const float az = fmaxf(0.0f, (fz + (float)(oz - 1)) * cell - slack);
+        if (axy2 + az * az > bd) break;
+        zlo = cz - oz;
+      }
+      const int row = (ix * g.dim[1] + iy) * g.dim[2];
+      if (ox == 0 && oy == 0) {
+        // two separate runs around the already scanned centre cell
+        const int a0 = max(zlo, 0), a1 = min(cz - 1, g.dim[2] - 1);
+        if (a0 <= a1) nn_scan(g, __ldg(&g.cell_start[row + a0]), __ldg(&g.cell_start[row + a1 + 1]), qx, qy, qz, bd, best, best_idx);
+        const int b0 = max(cz + 1, 0), b1 = min(zhi, g.dim[2] - 1);
+        if (b0 <= b1) nn_scan(g, __ldg(&g.cell_start[row + b0]), __ldg(&g.cell_start[row + b1 + 1]), qx, qy, qz, bd, best, best_idx);
+      } else {
+        const int a0 = max(zlo, 0), a1 = min(zhi, g.dim[2] - 1);
+        if (a0 <= a1) nn_scan(g, __ldg(&g.cell_start[row + a0]), __ldg(&g.cell_start[row + a1 + 1]), qx, qy, qz, bd, best, best_idx);
+      }
     }
   }
   best_d2 = bd;
@@ -176,7 +184,7 @@ __device__ bool solve6(double* A, double* b, double* x) {
 //   4. CTA partial -> global; the pair's last CTA sums the partials in index order, solves the 6x6 system,
 //      builds T_inc = Rz Ry Rx + t, updates final = T_inc * final and evaluates the convergence criteria.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 3) icp_iter_kernel(PairState* states, double max_d2, int max_iter, double eps,
+__global__ void __launch_bounds__(kThreads, 6) icp_iter_kernel(PairState* states, double max_d2, int max_iter, double eps,
                                                             int fixed_iters) {
   PairState& S = states[blockIdx.y];
   if (blockIdx.x >= S.nblocks || S.done) return;
