@@ -119,7 +119,8 @@ struct App {
     const size_t npix = (size_t)cols * rows;
     const int chunk_frames = 32;
     std::vector<uint16_t> buf(npix * chunk_frames), batch(npix * chunk_frames);
-    std::vector<double> poses(16 * chunk_frames);
+    std::vector<double> poses(16 * chunk_frames), segs(16 * chunk_frames);
+    std::vector<int> chunks(chunk_frames);
     while (!exit_) {
       const int got = src.read(buf.data(), chunk_frames);
       if (got == 0) break;                                    // end of stream
@@ -128,19 +129,24 @@ struct App {
         frame_id++;                                           // FrameID is 1-based (IntegrateApp.cpp:185)
         if (!gate(frame_id)) continue;
         const double* T = traj.data[frame_id - 1].T;
-        if (ctr_num > 0) {
-          const int chunk = (frame_id - 1) / ctr_interval;
-          if (er_tsdf_integrate_ctr(vol, buf.data() + npix * i, T, traj.data[0].T, seg_traj.data[0].T,
-                                    seg_traj.data[frame_id - 1].T, chunk))
-            return fail("er_tsdf_integrate_ctr");
-        } else {
-          std::memcpy(batch.data() + npix * nb, buf.data() + npix * i, sizeof(uint16_t) * npix);
-          std::memcpy(poses.data() + 16 * nb, T, sizeof(double) * 16);
-          nb++;
+        std::memcpy(batch.data() + npix * nb, buf.data() + npix * i, sizeof(uint16_t) * npix);
+        std::memcpy(poses.data() + 16 * nb, T, sizeof(double) * 16);
+        if (ctr_num > 0) {                                    // Reproject() inputs of this frame (IntegrateApp.cpp:241-242)
+          std::memcpy(segs.data() + 16 * nb, seg_traj.data[frame_id - 1].T, sizeof(double) * 16);
+          chunks[nb] = (frame_id - 1) / ctr_interval;
         }
+        nb++;
         processed++;
       }
-      if (nb > 0 && er_tsdf_integrate_batch(vol, batch.data(), poses.data(), nb)) return fail("er_tsdf_integrate_batch");
+      if (nb > 0) {
+        if (ctr_num > 0) {
+          if (er_tsdf_integrate_ctr_batch(vol, batch.data(), poses.data(), traj.data[0].T, seg_traj.data[0].T, segs.data(),
+                                          chunks.data(), nb))
+            return fail("er_tsdf_integrate_ctr_batch");
+        } else if (er_tsdf_integrate_batch(vol, batch.data(), poses.data(), nb)) {
+          return fail("er_tsdf_integrate_batch");
+        }
+      }
     }
     return er_tsdf_sync(vol) == 0 || fail("er_tsdf_sync");
   }

@@ -44,6 +44,7 @@ SIGNATURES = {
     "er_tsdf_reproject": (C.c_int, [C.c_void_p, c_u16p, c_dp, c_dp, c_dp, c_dp, C.c_int]),
     "er_tsdf_integrate": (C.c_int, [C.c_void_p, c_u16p, c_dp]),
     "er_tsdf_integrate_ctr": (C.c_int, [C.c_void_p, c_u16p, c_dp, c_dp, c_dp, c_dp, C.c_int]),
+    "er_tsdf_integrate_ctr_batch": (C.c_int, [C.c_void_p, c_u16p, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int]),
     "er_tsdf_integrate_batch": (C.c_int, [C.c_void_p, c_u16p, c_dp, C.c_int]),
     "er_tsdf_integrate_device": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, C.c_int]),
     "er_tsdf_profile_device": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, C.c_int, c_fp, c_fp, c_fp]),
@@ -230,6 +231,17 @@ class TSDFVolume:
         d = np.ascontiguousarray(depth, dtype=np.uint16)
         _check(lib().er_tsdf_integrate_ctr(self._h, _u16p(d), _dp(_mat(Ti)), _dp(_mat(T0)), _dp(_mat(A0)),
                                            _dp(_mat(Ai)), int(chunk)))
+
+    def integrate_ctr_batch(self, depth, Ti, T0, A0, Ai, chunks):
+        """Reproject + ScaleDepth + Integrate for n frames in batches (IntegrateApp.cpp:217-225 per frame)."""
+        d = np.ascontiguousarray(depth, dtype=np.uint16)
+        Ti = np.ascontiguousarray(Ti, dtype=np.float64).reshape(-1, 16)
+        Ai = np.ascontiguousarray(Ai, dtype=np.float64).reshape(-1, 16)
+        ch = np.ascontiguousarray(chunks, dtype=np.int32)
+        n = len(ch)
+        assert Ti.shape[0] == n and Ai.shape[0] == n and d.size == n * self.cols * self.rows
+        _check(lib().er_tsdf_integrate_ctr_batch(self._h, _u16p(d), _dp(Ti), _dp(_mat(T0)), _dp(_mat(A0)), _dp(Ai),
+                                                 ch.ctypes.data_as(c_ip), n))
 
     def sync(self):
         _check(lib().er_tsdf_sync(self._h))

@@ -86,6 +86,10 @@ int er_tsdf_integrate(er_tsdf* v, const uint16_t* depth, const double T[16]);
 /* Reproject + ScaleDepth + Integrate without the host round trip (IntegrateApp.cpp:217-225). */
 int er_tsdf_integrate_ctr(er_tsdf* v, const uint16_t* depth, const double Ti[16], const double T0[16],
                           const double A0[16], const double Ai[16], int chunk);
+/* The same for nframes consecutive frames (Ti, Ai = nframes*16 doubles, chunk = nframes ints), batched like
+ * er_tsdf_integrate_batch: this is how the 5000-frame ControlGrid configuration is fed. */
+int er_tsdf_integrate_ctr_batch(er_tsdf* v, const uint16_t* depth, const double* Ti, const double T0[16],
+                                const double A0[16], const double* Ai, const int* chunk, int nframes);
 /* nframes consecutive frames from host memory (depth = nframes*rows*cols, T = nframes*16), in order. */
 int er_tsdf_integrate_batch(er_tsdf* v, const uint16_t* depth, const double* T, int nframes);
 /* Same with the frames already resident in HBM (d_depth is a device pointer). */

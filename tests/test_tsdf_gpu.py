@@ -101,6 +101,20 @@ def test_fused_ctr_path_equals_two_step(oracle):
     assert np.array_equal(wa.view(np.uint32), wb.view(np.uint32))
 
 
+def test_ctr_batch_equals_per_frame_and_oracle(oracle):
+    sc = helpers.scene_ctr(num=3, interval=4)
+    traj = helpers.compose_traj(sc["pose_traj"], sc["seg_traj"], sc["interval"], capi.mat4_mul)
+    n = 11                                               # frames 1..11 (frame 12 would hit the trajectory end)
+    ovol = oracle.OracleTSDF()
+    helpers.run_app(ovol, sc["frames"][:n], traj, sc["seg_traj"], sc["grids"], sc["res"], sc["length"], sc["interval"])
+    g = capi.TSDFVolume(max_blocks=512)
+    g.set_control_grids(sc["grids"], sc["res"], sc["length"])
+    g.set_fusion(4)
+    chunks = [(fid - 1) // sc["interval"] for fid in range(1, n + 1)]
+    g.integrate_ctr_batch(sc["frames"][:n], traj[:n], traj[0], sc["seg_traj"][0], sc["seg_traj"][:n], chunks)
+    compare_blocks(ovol, g)
+
+
 def test_batch_and_device_paths_equal_per_frame(oracle):
     import torch
     sc = helpers.scene_room(n=6)
