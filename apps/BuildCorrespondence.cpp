@@ -162,9 +162,13 @@ struct CorresApp {
       }
     }
     const double cell = std::max(reg_dist, dist_thresh);
+#pragma omp parallel for num_threads(8) schedule(dynamic)
     for (int i = 0; i < num; i++) {
       clouds[i] = er_cloud_upload(device, pointclouds[i].xyz.data(), pointclouds[i].nrm.data(), pointclouds[i].size(), cell);
-      if (!clouds[i]) { std::cerr << "er_cloud_upload: " << er_last_error() << std::endl; ok = false; }
+      if (!clouds[i]) {
+#pragma omp critical
+        { std::cerr << "er_cloud_upload: " << er_last_error() << std::endl; ok = false; }
+      }
     }
     return ok;
   }

@@ -51,7 +51,10 @@ def run(local: int, rank: int, world: int, barrier, peak_gbs: float = 0.0, cpu_p
     # ---- e2e: host buffers -> upload (H2D + grid build) -> align -> poses back on the host
     barrier()
     t0 = time.perf_counter()
-    clouds = [capi.Cloud(x, n, device=local, cell_size=REG_DIST) for (x, n) in frags]
+    # fragments are uploaded from 8 host threads, like the reference loads them (omp parallel for, CorresApp.cpp:82)
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        clouds = list(ex.map(lambda xn: capi.Cloud(xn[0], xn[1], device=local, cell_size=REG_DIST), frags))
     T, its, fit = capi.icp_align_batch(clouds, tgt, src, Tinit, REG_DIST, ITERS, 1e-6, True)
     barrier()
     e2e_s = time.perf_counter() - t0
