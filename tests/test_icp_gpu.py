@@ -74,3 +74,24 @@ def test_empty_and_tiny_clouds():
     assert len(pairs) == 2
     with pytest.raises(capi.ElasticError):
         capi.icp_align(big, tiny, np.eye(4), max_dist=0.5)        # radius larger than the grid cell
+
+
+def test_partial_overlap_and_large_offsets(oracle):
+    """Only part of the source has neighbours within the gate, and the first iterations have large residuals (the
+    pruned neighbourhood search must still return the exact nearest neighbour)."""
+    xyz0, n0 = synth.make_fragment(0, 40000)
+    xyz1, n1 = synth.make_fragment(1, 40000)
+    keep = xyz1[:, 0] + xyz1[:, 1] < 2.2                       # drop a corner region of the source
+    xyz1, n1 = xyz1[keep], n1[keep]
+    xyz1 = xyz1 + np.where(xyz1[:, 2:3] > 1.0, np.float32(0.08), np.float32(0.0))   # push a slab out of reach
+    to, so = oracle.OracleCloud(xyz0, n0, 0.03), oracle.OracleCloud(xyz1, n1, 0.03)
+    tg, sg = capi.Cloud(xyz0, n0, cell_size=0.03), capi.Cloud(xyz1, n1, cell_size=0.03)
+    for seed in (21, 22):
+        P = synth.perturbation(seed, max_rot_deg=2.5, max_trans=0.02)
+        assert oracle.icp_count_inliers(to, so, P, 0.03) == capi.icp_count_inliers(tg, sg, P, 0.03)
+        To, ito, fo, _ = oracle.icp_align(to, so, P, 0.03, 20, 1e-6, False)
+        Tg, itg, fg = capi.icp_align(tg, sg, P, 0.03, 20, 1e-6, False)
+        assert ito == itg and np.linalg.norm(To - Tg) <= POSE_TOL
+        po, io = oracle.icp_correspondences(to, so, To, 0.015, 0.8660)
+        pg, ig = capi.icp_correspondences(tg, sg, To, 0.015, 0.8660)
+        assert np.array_equal(po, pg) and np.allclose(io, ig, rtol=1e-10, atol=1e-6)
