@@ -40,7 +40,7 @@ SIGNATURES = {
     "er_tsdf_set_partition": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     "er_tsdf_set_stats": (C.c_int, [C.c_void_p, C.c_int]),
     "er_tsdf_get_stats": (C.c_int, [C.c_void_p, c_u64p, c_u64p, c_u64p]),
-    "er_tsdf_get_class_stats": (C.c_int, [C.c_void_p, c_u64p, c_u64p]),
+    "er_tsdf_get_class_stats": (C.c_int, [C.c_void_p, c_u64p, c_u64p, c_u64p, c_u64p]),
     "er_tsdf_reproject": (C.c_int, [C.c_void_p, c_u16p, c_dp, c_dp, c_dp, c_dp, C.c_int]),
     "er_tsdf_integrate": (C.c_int, [C.c_void_p, c_u16p, c_dp]),
     "er_tsdf_integrate_ctr": (C.c_int, [C.c_void_p, c_u16p, c_dp, c_dp, c_dp, c_dp, C.c_int]),
@@ -175,9 +175,10 @@ class TSDFVolume:
     def stats(self):
         a, b, c = C.c_uint64(), C.c_uint64(), C.c_uint64()
         _check(lib().er_tsdf_get_stats(self._h, C.byref(a), C.byref(b), C.byref(c)))
-        o, fl = C.c_uint64(), C.c_uint64()
-        _check(lib().er_tsdf_get_class_stats(self._h, C.byref(o), C.byref(fl)))
-        return dict(frames=a.value, touched_blocks=b.value, updated_voxels=c.value, one_pairs=o.value, full_pairs=fl.value)
+        o, fl, idle, allone = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(lib().er_tsdf_get_class_stats(self._h, C.byref(o), C.byref(fl), C.byref(idle), C.byref(allone)))
+        return dict(frames=a.value, touched_blocks=b.value, updated_voxels=c.value, one_pairs=o.value, full_pairs=fl.value,
+                    full_idle_pairs=idle.value, full_all_one_pairs=allone.value)
 
     # -- the hot path
     def integrate(self, depth, T):

@@ -73,7 +73,8 @@ int er_tsdf_set_stats(er_tsdf* v, int enable);
 int er_tsdf_get_stats(er_tsdf* v, uint64_t* frames, uint64_t* touched_blocks, uint64_t* updated_voxels);
 /* With stats enabled: how many (4^3 sub-brick, frame) pairs took the free-space shortcut (every voxel gets tsdf = 1)
  * and how many the exact per-voxel path; every other pair was skipped as provably unchanged. */
-int er_tsdf_get_class_stats(er_tsdf* v, uint64_t* one_pairs, uint64_t* full_pairs);
+int er_tsdf_get_class_stats(er_tsdf* v, uint64_t* one_pairs, uint64_t* full_pairs, uint64_t* full_idle,
+                            uint64_t* full_all_one);   /* last two (optional): exact-path pairs that updated nothing / only with tsdf = 1 */
 
 /* CIntegrateApp::Reproject (IntegrateApp.cpp:228-269) on one frame: depth is rewritten in place.
  * Ti = traj[frame-1], T0 = traj[0], A0 = seg_traj[0], Ai = seg_traj[frame-1], chunk = (frame-1)/interval. */

@@ -38,7 +38,18 @@ def run(tag, env, fusion=32, reps=4):
     del vol
 
 
+def class_stats():
+    vol = capi.TSDFVolume(max_blocks=1024)
+    vol.integrate_device(d.data_ptr(), poses, n)
+    vol.set_stats(True)
+    s0 = vol.stats()
+    vol.integrate_device(d.data_ptr(), poses, n)
+    s1 = vol.stats()
+    print({k: (s1[k] - s0[k]) / n for k in s1 if k != "frames"}, flush=True)
+
+
 if __name__ == "__main__":
+    class_stats()
     run("minb4 fusion32", {"ER_INT_MINB": "4"})
     run("minb5 fusion32", {"ER_INT_MINB": "5"})
     run("minb6 fusion32", {"ER_INT_MINB": "6"})
