@@ -49,9 +49,7 @@ def class_stats():
 
 
 if __name__ == "__main__":
-    class_stats()
-    run("minb4 fusion32", {"ER_INT_MINB": "4"})
-    run("minb5 fusion32", {"ER_INT_MINB": "5"})
-    run("minb6 fusion32", {"ER_INT_MINB": "6"})
-    run("minb4 fusion16", {"ER_INT_MINB": "4"}, fusion=16)
-    run("minb4 fusion8", {"ER_INT_MINB": "4"}, fusion=8)
+    # python tools/time_tsdf.py 256 ER_INT_THREADS=256 ER_INT_THREADS=128 ...   (one run per KEY=VALUE[,KEY=VALUE])
+    for spec in sys.argv[2:] or [""]:
+        env = dict(kv.split("=") for kv in spec.split(",") if kv)
+        run(spec or "default", env)
