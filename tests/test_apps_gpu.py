@@ -166,3 +166,49 @@ def test_buildcorrespondence_traj_mode_creates_candidates(tmp_path):
     assert rc == 0 and "3 initial matching candidates are created." in out, out
     got = parse_log(os.path.join(cwd, "reg_output.log"))
     assert [g[0][:2] for g in got] == [[0, 1], [0, 2], [1, 2]]
+
+
+def test_integrate_cli_skips_flagged_frames(oracle, tmp_path):
+    """A trajectory record with frame_ == -1 is skipped (IntegrateApp.cpp:196)."""
+    sc = helpers.scene_room(n=5)
+    d = str(tmp_path)
+    synth.write_depth_container(os.path.join(d, "depth.raw"), sc["frames"])
+    ids = [(i, i, -1 if i in (1, 3) else i + 1) for i in range(len(sc["traj"]))]
+    synth.write_log(os.path.join(d, "traj.log"), sc["traj"], ids=ids)
+    rc, out = run([os.path.join(BIN, "Integrate"), "-oni", os.path.join(d, "depth.raw"), "--ref_traj",
+                   os.path.join(d, "traj.log"), "--save_to", os.path.join(d, "w.pcd")], d)
+    assert rc == 0, out
+    vol = oracle.OracleTSDF()
+    helpers.run_app(vol, sc["frames"], sc["traj"], frame_flags=[f for (_, _, f) in ids])
+    ref = oracle.sort_world(vol.extract())
+    mine = oracle.sort_world(synth.read_pcd_xyzi(os.path.join(d, "w.pcd")))
+    assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32))
+
+
+def test_buildcorrespondence_blacklist_and_redux(oracle, tmp_path):
+    """--blacklist drops every pair touching a listed fragment (CorresApp.cpp:222-229); --redux replaces the ICP
+    result of listed pairs by the given transform (CorresApp.cpp:283-293) without running ICP on them."""
+    d = str(tmp_path / "data")
+    os.makedirs(d)
+    n_frag = 3
+    frags = [synth.make_local_fragment(i, 20000) for i in range(n_frag)]
+    for i, (x, n) in enumerate(frags):
+        synth.write_pcd_xyzrgbnormal(os.path.join(d, "cloud_bin_%d.pcd" % i), x, n)
+    pairs = [(0, 1), (0, 2), (1, 2)]
+    Tinit = [synth.quantize_log(synth.pair_init(i, j)) for (i, j) in pairs]
+    synth.write_log(os.path.join(d, "pairs.log"), np.array(Tinit), ids=[(i, j, n_frag) for (i, j) in pairs])
+    with open(os.path.join(d, "black.txt"), "w") as f:
+        f.write("# fragments to ignore\n2\n")
+    marker = synth.quantize_log(Tinit[0] @ synth.make_pose(np.eye(3), [0.001, 0.0, 0.0]))
+    synth.write_log(os.path.join(d, "redux.log"), np.array([marker]), ids=[(0, 1, 3)])
+    cwd = str(tmp_path / "run")
+    os.makedirs(cwd)
+    rc, out = run([os.path.join(BIN, "BuildCorrespondence"), "--reg_traj", os.path.join(d, "pairs.log"), "--registration",
+                   "--reg_num", "2000", "--blacklist", os.path.join(d, "black.txt"), "--redux", os.path.join(d, "redux.log")], cwd)
+    assert rc == 0, out
+    got = parse_log(os.path.join(cwd, "reg_output.log"))
+    assert [g[0][:2] for g in got] == [[0, 1], [0, 2], [1, 2]]
+    assert got[1][0][2] == -1 and got[2][0][2] == -1               # blacklisted pairs are rejected
+    assert np.allclose(got[0][1], marker, atol=5e-9)                # redux transform taken verbatim, no ICP
+    assert got[0][0][2] > 0
+    assert not os.path.exists(os.path.join(d, "corres_0_2.txt")) and os.path.exists(os.path.join(d, "corres_0_1.txt"))
