@@ -27,6 +27,7 @@
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <mutex>
@@ -538,6 +539,7 @@ er_cloud* er_cloud_upload(int device, const float* xyz, const float* normals, si
   if (n == 0) for (int a = 0; a < 3; a++) lo[a] = hi[a] = 0.f;
   // cells of half the admissible radius (a hair more), searched two rings deep: fewer candidates per cell
   int rings = 2;
+  if (const char* e = std::getenv("ER_ICP_RINGS")) rings = std::max(1, std::min(6, std::atoi(e)));   // experiment knob
   double cell = cell_size * 1.001 / rings;
   int dim[3];
   for (;;) {
