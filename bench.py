@@ -232,6 +232,8 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
+    # NCCL prints its version banner to stdout when NCCL_DEBUG is set; stdout carries exactly one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     import torch
     import torch.distributed as dist
     from elasticreconstruction_b200 import capi
