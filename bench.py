@@ -232,8 +232,11 @@ def main():
     if args.impl == "reference":
         return run_reference(args)
 
-    # NCCL prints its version banner to stdout when NCCL_DEBUG is set; stdout carries exactly one JSON line
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+    # stdout must carry exactly one JSON line, but NCCL prints its version banner to stdout when NCCL_DEBUG is set
+    # (and libraries may print there too): park the real stdout and point fd 1 at stderr until the line is written
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from elasticreconstruction_b200 import capi
@@ -384,7 +387,8 @@ def main():
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "wall_s_timed_region": wall, "icp": icp,
         }
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0
