@@ -6,7 +6,9 @@
 // numeric work (ScaleDepth, Integrate, Reproject, SaveWorld) is the library's.  Differences, all at the edges:
 //   * "-oni <file>" names the raw depth container of apps/er_io.h (OpenNI is not available); "-dev" cannot open;
 //   * frames are pulled synchronously, so there is no 10 x 300 ms end-of-stream timeout;
-//   * extra flags: --device N, --max_blocks N, --fusion N (frames per fused launch), --bench_json FILE.
+//   * extra flags: --device N, --max_blocks N, --fusion N (frames per fused launch), --bench_json FILE, and
+//     --voxel_size M / --tsdf_trunc M / --block_res 64: the reference's constructor constants
+//     (TSDFVolume.cpp:10-11,57), defaulting to the reference values 3/512, 0.03, 64.
 #include <chrono>
 #include <cstdio>
 #include <iostream>
@@ -37,6 +39,7 @@ static int print_help() {
   std::cout << "    -dev <device> (default), -oni <oni_file>" << std::endl;
   std::cout << "B200 build only:" << std::endl;
   std::cout << "    --device <n> --max_blocks <n> --fusion <1..32> --bench_json <file>" << std::endl;
+  std::cout << "    --voxel_size <m> (3/512) --tsdf_trunc <m> (0.03) --block_res <n> (64, fixed)" << std::endl;
   return 0;
 }
 
@@ -45,7 +48,8 @@ struct App {
   std::string traj_filename, pose_filename, seg_filename, camera_filename, ctr_filename, pcd_filename = "world.pcd";
   int ctr_num = 0, ctr_resolution = 8, ctr_interval = 50, start_from = -1, end_at = 100000000;
   double ctr_length = 3.0;
-  int device = 0, max_blocks = 4096, fusion = 32;
+  int device = 0, max_blocks = 4096, fusion = 32, block_res = 64;
+  double voxel_size = 0.0, tsdf_trunc = 0.0;               // 0 = the reference constants
   std::string bench_json;
 
   CameraParam camera;
@@ -92,7 +96,7 @@ struct App {
         std::fprintf(stderr, "Trajectory created from pose and segment trajectories.\n");
       }
     }
-    vol = er_tsdf_create(device, cols, rows, 0.0, 64, 0.0, (size_t)max_blocks);
+    vol = er_tsdf_create(device, cols, rows, voxel_size, block_res, tsdf_trunc, (size_t)max_blocks);
     if (!vol) return fail("er_tsdf_create");
     if (er_tsdf_set_camera(vol, camera.fx, camera.fy, camera.cx, camera.cy, camera.integration_trunc)) return fail("set_camera");
     if (er_tsdf_set_fusion(vol, fusion)) return fail("set_fusion");
@@ -195,6 +199,9 @@ int main(int argc, char* argv[]) {
   parse_argument(argc, argv, "--max_blocks", app.max_blocks);
   parse_argument(argc, argv, "--fusion", app.fusion);
   parse_argument(argc, argv, "--bench_json", app.bench_json);
+  parse_argument(argc, argv, "--voxel_size", app.voxel_size);
+  parse_argument(argc, argv, "--tsdf_trunc", app.tsdf_trunc);
+  parse_argument(argc, argv, "--block_res", app.block_res);
 
   std::cout << "Registration mode: On" << std::endl;
   const auto t0 = std::chrono::steady_clock::now();

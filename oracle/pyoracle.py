@@ -14,6 +14,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 REF_INTEGRATE = os.path.join(_HERE, "_ref", "Integrate_ref")
+REF_INTEGRATE_12MM = os.path.join(_HERE, "_ref", "Integrate_ref_12mm")     # unit_length_ patched to 0.012 (Makefile: ref12)
 
 _lib = None
 
@@ -26,6 +27,8 @@ def build(force: bool = False) -> None:
         subprocess.check_call(["make", "-C", _HERE, "-s", "_build/liboracle.so"])
     if os.path.isdir("/root/reference/Integrate") and (force or not os.path.exists(REF_INTEGRATE)):
         subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+    if os.path.isdir("/root/reference/Integrate") and (force or not os.path.exists(REF_INTEGRATE_12MM)):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref12"])
 
 
 def lib():
@@ -277,12 +280,12 @@ def world_digest(xyzi: np.ndarray) -> str:
     return hashlib.sha256(sort_world(xyzi).tobytes()).hexdigest()
 
 
-def run_reference_integrate(args, cwd=None, timing: bool = False):
+def run_reference_integrate(args, cwd=None, timing: bool = False, binary: str = None):
     """Run the verbatim reference binary (oracle/_ref/Integrate_ref).  Returns (stdout+stderr, ms_per_frame)."""
     env = dict(os.environ)
     if timing:
         env["ER_SHIM_TIMING"] = "1"
-    p = subprocess.run([REF_INTEGRATE] + list(args), cwd=cwd, env=env, stdout=subprocess.PIPE,
+    p = subprocess.run([binary or REF_INTEGRATE] + list(args), cwd=cwd, env=env, stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, check=True)
     ms = None
     for line in p.stdout.splitlines():

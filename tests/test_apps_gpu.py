@@ -52,6 +52,29 @@ def test_integrate_cli_matches_reference_binary(oracle, tmp_path, mk):
     assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32))
 
 
+def test_integrate_cli_12mm_voxels(oracle, tmp_path):
+    """BASELINE.json configs[0] (10 frames, identity .log, 12 mm voxels): --voxel_size against the reference binary
+    built with its unit_length_ constant rewritten to 0.012 (oracle/Makefile ref12), else against the oracle."""
+    sc = helpers.scene_wall(n=10)
+    d = str(tmp_path)
+    args = helpers.write_scene(sc, d)
+    mine_pcd = os.path.join(d, "mine.pcd")
+    my_args = [a if a != os.path.join(d, "world.pcd") else mine_pcd for a in args] + ["--voxel_size", "0.012"]
+    rc, out = run([os.path.join(BIN, "Integrate")] + my_args, d)
+    assert rc == 0 and "Total 10 frames processed." in out, out
+    mine = oracle.sort_world(synth.read_pcd_xyzi(mine_pcd))
+    if os.path.exists(oracle.REF_INTEGRATE_12MM):
+        oracle.run_reference_integrate(args, cwd=d, binary=oracle.REF_INTEGRATE_12MM)
+        ref = oracle.sort_world(synth.read_pcd_xyzi(os.path.join(d, "world.pcd")))
+    else:
+        vol = oracle.OracleTSDF()
+        vol.set_voxel(0.012, 0.03)
+        helpers.run_scene(vol, sc, mul=oracle.mat4_mul)
+        ref = oracle.sort_world(vol.extract())
+    assert mine.shape == ref.shape
+    assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32))
+
+
 def test_integrate_cli_help_and_bad_source(tmp_path):
     rc, out = run([os.path.join(BIN, "Integrate")], str(tmp_path))
     assert rc == 0 and "--ref_traj <log_file>" in out            # no arguments: help, rc 0 (Integrate.cpp:37-39)

@@ -48,6 +48,26 @@ def test_oracle_matches_live_reference(oracle, mk):
     assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32))
 
 
+def test_oracle_12mm_matches_patched_reference(oracle):
+    """BASELINE.json configs[0]: 10 frames 640x480, identity .log, 12 mm voxels.  The reference can only do 12 mm with
+    its constructor constant edited; oracle/Makefile target ref12 builds exactly that (one sed on unit_length_).  Pins
+    the oracle's set_voxel() path, which the custom-voxel GPU parity test relies on."""
+    if not os.path.exists(oracle.REF_INTEGRATE_12MM):
+        pytest.skip("oracle/_ref/Integrate_ref_12mm not built (needs /root/reference at build time)")
+    sc = helpers.scene_wall(n=10)
+    with tempfile.TemporaryDirectory() as d:
+        args = helpers.write_scene(sc, d)
+        out, _ = oracle.run_reference_integrate(args, cwd=d, binary=oracle.REF_INTEGRATE_12MM)
+        ref = oracle.sort_world(synth.read_pcd_xyzi(os.path.join(d, "world.pcd")))
+    assert "Total 10 frames processed." in out
+    vol = oracle.OracleTSDF()
+    vol.set_voxel(0.012, 0.03)
+    helpers.run_scene(vol, sc, mul=oracle.mat4_mul)
+    mine = oracle.sort_world(vol.extract())
+    assert len(ref) > 50000 and mine.shape == ref.shape
+    assert np.array_equal(mine.view(np.uint32), ref.view(np.uint32))
+
+
 def test_inverse_is_an_inverse(oracle):
     rng = np.random.default_rng(1)
     for _ in range(50):
