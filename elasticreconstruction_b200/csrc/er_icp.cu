@@ -43,11 +43,16 @@ constexpr int kPtsPerThread = 8;
 constexpr int kPtsPerCta = kThreads * kPtsPerThread;
 constexpr int kAcc = 29;               // 21 (upper ATA) + 6 (ATb) + sum d^2 + count
 constexpr int kMaxEvents = 16;
+constexpr int kMaxRings = 2;           // cooperative search: at most (2*2+1)^2 + 1 = 26 cell-column items per query
+constexpr int kMaxItems = 32 * ((2 * kMaxRings + 1) * (2 * kMaxRings + 1) + 1);
+constexpr int kNoMatch = 0x7fffffff;
 
 struct GridDev {
   const float4* pts;      // sorted by cell: x, y, z, original index (int bits)
   const float4* nrm;      // same order
   const int* cell_start;  // ncell + 1
+  const float* xyz_orig;  // the same points / normals in original order (3 floats each)
+  const float* nrm_orig;
   float org[3];
   float inv_cell;
   float cell;
@@ -74,14 +79,28 @@ struct PairState {
 // its lower distance bound (computed from the query's position inside its cell, minus a slack that covers the
 // float rounding of the cell assignment) does not exceed the best distance so far -- so a converged pair scans
 // a handful of candidates instead of the full neighbourhood, with the same result as the exhaustive scan.
+__device__ __forceinline__ void nn_consider(const float4 p, int s, float qx, float qy, float qz, float& bd, int& best, int& best_idx) {
+  const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+  const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+  const int idx = __float_as_int(p.w);
+  if (d2 < bd || (d2 == bd && idx < best_idx)) { bd = d2; best = s; best_idx = idx; }
+}
+
+// candidates s0..s1-1, four loads in flight at a time (the scan is latency-bound: one cell holds only a handful of
+// points).  Slots past the end re-read the run's last point, which cannot change the result.
 __device__ __forceinline__ void nn_scan(const GridDev& g, int s0, int s1, float qx, float qy, float qz, float& bd, int& best,
                                         int& best_idx) {
-  for (int s = s0; s < s1; s++) {
-    const float4 p = __ldg(&g.pts[s]);
-    const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
-    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-    const int idx = __float_as_int(p.w);
-    if (d2 < bd || (d2 == bd && idx < best_idx)) { bd = d2; best = s; best_idx = idx; }
+  const int last = s1 - 1;
+  for (int s = s0; s < s1; s += 4) {
+    const int t1 = min(s + 1, last), t2 = min(s + 2, last), t3 = min(s + 3, last);
+    const float4 p0 = __ldg(&g.pts[s]);
+    const float4 p1 = __ldg(&g.pts[t1]);
+    const float4 p2 = __ldg(&g.pts[t2]);
+    const float4 p3 = __ldg(&g.pts[t3]);
+    nn_consider(p0, s, qx, qy, qz, bd, best, best_idx);
+    nn_consider(p1, t1, qx, qy, qz, bd, best, best_idx);
+    nn_consider(p2, t2, qx, qy, qz, bd, best, best_idx);
+    nn_consider(p3, t3, qx, qy, qz, bd, best, best_idx);
   }
 }
 
@@ -184,9 +203,87 @@ __device__ bool solve6(double* A, double* b, double* x) {
 //   3. point-to-plane row [s x n, n], d = n.(t - s), accumulate A^T A / A^T b in double   (LLS)
 //   4. CTA partial -> global; the pair's last CTA sums the partials in index order, solves the 6x6 system,
 //      builds T_inc = Rz Ry Rx + t, updates final = T_inc * final and evaluates the convergence criteria.
+//
+// Step 2 comes in two forms with identical results (the exact nearest neighbour, ties to the smallest original
+// index, is independent of the visiting order):
+//   COOP = false  every thread walks the pruned neighbourhood of its own query (nn_search); lanes of a warp have
+//                 very different trip counts (measured 11.7 of 32 lanes active on average);
+//   COOP = true   warp-cooperative: each lane scans only its query's own cell, which gives a bound bd, and lists
+//                 the cell columns (x, y offsets) that can still hold something as close as bd -- usually one to
+//                 four -- as items (lane, ox, oy) in a per-warp list in shared memory.  The items are then dealt
+//                 round-robin to the lanes regardless of the query they belong to: a lane derives the column's run of
+//                 z cells from the owning query's freshest bound, scans it and merges the best candidate into the
+//                 query's 64-bit key (float bits of d^2 << 32 | original index) with atomicMin in shared memory.
+//                 The warp's work is thereby balanced over its lanes whatever the spread between its queries.
+// A match is kept as that 64-bit key; kNoMatch in the low word means none.  Candidates with d^2 above bd_init (the
+// float just above max_dist^2) can never be kept, so the search starts from that bound.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 6) icp_iter_kernel(PairState* states, double max_d2, int max_iter, double eps,
-                                                            int fixed_iters) {
+__device__ __forceinline__ unsigned long long pack_key(float d2, int idx) {
+  return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)idx;
+}
+
+// offset bound: distance from a query at fraction f of its cell to the slab `o` cells away (0 for its own slab)
+__device__ __forceinline__ float slab_gap(int o, float f, float cell, float slack) {
+  return fmaxf(0.0f, (o > 0 ? ((float)o - f) : (o < 0 ? (f - (float)(o + 1)) : 0.0f)) * cell - slack);
+}
+
+// The rows of one thread's accepted correspondences (keys[it * kThreads], source point k0 + it * kThreads), summed in
+// double and reduced over the warp by a fixed shuffle tree into out[].  PASS 0: the 15 sums of a, b, c against
+// (a, b, c, nx, ny, nz); PASS 1: the 6 n.n sums, the 6 right-hand sides, sum of d^2 and the count.
+template <int PASS>
+__device__ __forceinline__ void icp_rows(const PairState& S, const GridDev& g, const unsigned long long* keys, int k0,
+                                         double max_d2, double* out, int lane) {
+  constexpr int N = PASS == 0 ? 15 : 14;
+  double acc[N];
+#pragma unroll
+  for (int i = 0; i < N; i++) acc[i] = 0.0;
+#pragma unroll 1
+  for (int it = 0; it < kPtsPerThread; it++) {
+    const unsigned long long key = keys[it * kThreads];
+    const int idx = (int)(unsigned)(key & 0xffffffffu);
+    const float md2 = __uint_as_float((unsigned)(key >> 32));
+    if (idx == kNoMatch || (double)md2 > max_d2) continue;
+    const float* cp = S.cur + 3 * (size_t)(k0 + it * kThreads);
+    const float sx = cp[0], sy = cp[1], sz = cp[2];
+    const float* tp = g.xyz_orig + 3 * (size_t)idx;
+    const float* np = g.nrm_orig + 3 * (size_t)idx;
+    const float dx = __ldg(tp), dy = __ldg(tp + 1), dz = __ldg(tp + 2), nx = __ldg(np), ny = __ldg(np + 1), nz = __ldg(np + 2);
+    if (PASS == 1) { acc[12] += (double)md2; acc[13] += 1.0; }
+    if (isfinite(sx) && isfinite(sy) && isfinite(sz) && isfinite(dx) && isfinite(dy) && isfinite(dz) && isfinite(nx) &&
+        isfinite(ny) && isfinite(nz)) {
+      // float expressions widened afterwards, as in PCL's estimateRigidTransformation (float operands)
+      const double a = (double)__fsub_rn(__fmul_rn(nz, sy), __fmul_rn(ny, sz));
+      const double b = (double)__fsub_rn(__fmul_rn(nx, sz), __fmul_rn(nz, sx));
+      const double c = (double)__fsub_rn(__fmul_rn(ny, sx), __fmul_rn(nx, sy));
+      const double dnx = (double)nx, dny = (double)ny, dnz = (double)nz;
+      if (PASS == 0) {
+        acc[0] += a * a;   acc[1] += a * b;   acc[2] += a * c;   acc[3] += a * dnx;  acc[4] += a * dny;  acc[5] += a * dnz;
+        acc[6] += b * b;   acc[7] += b * c;   acc[8] += b * dnx; acc[9] += b * dny;  acc[10] += b * dnz;
+        acc[11] += c * c;  acc[12] += c * dnx; acc[13] += c * dny; acc[14] += c * dnz;
+      } else {
+        float df = __fadd_rn(__fadd_rn(__fmul_rn(nx, dx), __fmul_rn(ny, dy)), __fmul_rn(nz, dz));
+        df = __fsub_rn(__fsub_rn(__fsub_rn(df, __fmul_rn(nx, sx)), __fmul_rn(ny, sy)), __fmul_rn(nz, sz));
+        const double d = (double)df;
+        acc[0] += (double)__fmul_rn(nx, nx); acc[1] += (double)__fmul_rn(nx, ny); acc[2] += (double)__fmul_rn(nx, nz);
+        acc[3] += (double)__fmul_rn(ny, ny); acc[4] += (double)__fmul_rn(ny, nz);
+        acc[5] += (double)__fmul_rn(nz, nz);
+        acc[6] += a * d;  acc[7] += b * d;  acc[8] += c * d;  acc[9] += dnx * d;  acc[10] += dny * d;  acc[11] += dnz * d;
+      }
+    }
+  }
+  // warp reduction (fixed tree); out[] is laid out as the 29 sums of the normal equations
+#pragma unroll
+  for (int i = 0; i < N; i++) {
+    double v = acc[i];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    if (lane == 0) out[PASS == 0 ? i : 15 + i] = v;
+  }
+}
+
+template <bool COOP, int MINB>
+__global__ void __launch_bounds__(kThreads, MINB) icp_iter_kernel(PairState* states, double max_d2, float bd_init, int max_iter,
+                                                            double eps, int fixed_iters) {
   PairState& S = states[blockIdx.y];
   if (blockIdx.x >= S.nblocks || S.done) return;
   __shared__ double s_part[kThreads / 32][kAcc];
@@ -199,69 +296,134 @@ __global__ void __launch_bounds__(kThreads, 6) icp_iter_kernel(PairState* states
 
   const int base = blockIdx.x * kPtsPerCta;
   // phase 1: move the points and search (the double accumulators are not live yet: lower register pressure)
-  __shared__ int s_match[kPtsPerThread][kThreads];
-  __shared__ float s_md2[kPtsPerThread][kThreads];
+  __shared__ unsigned long long s_key[kPtsPerThread][kThreads];
+  __shared__ unsigned short s_items[COOP ? kThreads / 32 : 1][COOP ? kMaxItems : 1];   // lane | ox+8 | oy+8 | upper
+  __shared__ int s_qi[COOP ? kThreads / 32 : 1][3][32];
+  __shared__ float s_qf[COOP ? kThreads / 32 : 1][6][32];
 #pragma unroll 1
   for (int it = 0; it < kPtsPerThread; it++) {
     const int k = base + it * kThreads + tid;
-    s_match[it][tid] = -1;
-    s_md2[it][tid] = 0.0f;
+    unsigned long long key = pack_key(bd_init, kNoMatch);
+    float sx = 0.0f, sy = 0.0f, sz = 0.0f;
     if (k < S.n_src) {
       float* cp = S.cur + 3 * (size_t)k;
       const float x = cp[0], y = cp[1], z = cp[2];
       // Matrix4f * (x, y, z, 1): ((m0*x + m1*y) + m2*z) + m3*1
-      const float sx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[0], x), __fmul_rn(M[1], y)), __fmul_rn(M[2], z)), M[3]);
-      const float sy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[4], x), __fmul_rn(M[5], y)), __fmul_rn(M[6], z)), M[7]);
-      const float sz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[8], x), __fmul_rn(M[9], y)), __fmul_rn(M[10], z)), M[11]);
+      sx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[0], x), __fmul_rn(M[1], y)), __fmul_rn(M[2], z)), M[3]);
+      sy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[4], x), __fmul_rn(M[5], y)), __fmul_rn(M[6], z)), M[7]);
+      sz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[8], x), __fmul_rn(M[9], y)), __fmul_rn(M[10], z)), M[11]);
       cp[0] = sx; cp[1] = sy; cp[2] = sz;
-      float d2;
-      const int m = nn_search(g, sx, sy, sz, d2);
-      if (m >= 0 && !((double)d2 > max_d2)) { s_match[it][tid] = m; s_md2[it][tid] = d2; }
     }
-  }
-  // phase 2: point-to-plane rows of the accepted correspondences
-  double acc[kAcc];
-#pragma unroll
-  for (int i = 0; i < kAcc; i++) acc[i] = 0.0;
-#pragma unroll 1
-  for (int it = 0; it < kPtsPerThread; it++) {
-    const int m = s_match[it][tid];
-    if (m < 0) continue;
-    const int k = base + it * kThreads + tid;
-    const float* cp = S.cur + 3 * (size_t)k;
-    const float sx = cp[0], sy = cp[1], sz = cp[2];
-    const float4 t = __ldg(&g.pts[m]);
-    const float4 nn = __ldg(&g.nrm[m]);
-    const float dx = t.x, dy = t.y, dz = t.z, nx = nn.x, ny = nn.y, nz = nn.z;
-    acc[27] += (double)s_md2[it][tid];
-    acc[28] += 1.0;
-    if (isfinite(sx) && isfinite(sy) && isfinite(sz) && isfinite(dx) && isfinite(dy) && isfinite(dz) && isfinite(nx) &&
-        isfinite(ny) && isfinite(nz)) {
-      // float expressions widened afterwards, as in PCL's estimateRigidTransformation (float operands)
-      const double a = (double)__fsub_rn(__fmul_rn(nz, sy), __fmul_rn(ny, sz));
-      const double b = (double)__fsub_rn(__fmul_rn(nx, sz), __fmul_rn(nz, sx));
-      const double c = (double)__fsub_rn(__fmul_rn(ny, sx), __fmul_rn(nx, sy));
-      float df = __fadd_rn(__fadd_rn(__fmul_rn(nx, dx), __fmul_rn(ny, dy)), __fmul_rn(nz, dz));
-      df = __fsub_rn(__fsub_rn(__fsub_rn(df, __fmul_rn(nx, sx)), __fmul_rn(ny, sy)), __fmul_rn(nz, sz));
-      const double d = (double)df;
-      const double dnx = (double)nx, dny = (double)ny, dnz = (double)nz;
-      acc[0] += a * a;   acc[1] += a * b;   acc[2] += a * c;   acc[3] += a * dnx;  acc[4] += a * dny;  acc[5] += a * dnz;
-      acc[6] += b * b;   acc[7] += b * c;   acc[8] += b * dnx; acc[9] += b * dny;  acc[10] += b * dnz;
-      acc[11] += c * c;  acc[12] += c * dnx; acc[13] += c * dny; acc[14] += c * dnz;
-      acc[15] += (double)__fmul_rn(nx, nx); acc[16] += (double)__fmul_rn(nx, ny); acc[17] += (double)__fmul_rn(nx, nz);
-      acc[18] += (double)__fmul_rn(ny, ny); acc[19] += (double)__fmul_rn(ny, nz);
-      acc[20] += (double)__fmul_rn(nz, nz);
-      acc[21] += a * d;  acc[22] += b * d;  acc[23] += c * d;  acc[24] += dnx * d;  acc[25] += dny * d;  acc[26] += dnz * d;
+    if (!COOP) {
+      if (k < S.n_src) {
+        float d2;
+        const int m = nn_search(g, sx, sy, sz, d2);
+        if (m >= 0) key = pack_key(d2, __float_as_int(__ldg(&g.pts[m]).w));
+      }
+      s_key[it][tid] = key;
+      continue;
     }
-  }
-  // ---- CTA reduction (fixed tree)
+    // ---- cooperative search
+    const int K = g.rings;
+    const float cell = g.cell, slack = 1e-5f * g.cell;
+    bool valid = false;
+    int cx = 0, cy = 0, cz = 0;
+    float fx = 0.0f, fy = 0.0f, fz = 0.0f, bd = bd_init;
+    if (k < S.n_src) {
+      const float lx = __fmul_rn(__fsub_rn(sx, g.org[0]), g.inv_cell);
+      const float ly = __fmul_rn(__fsub_rn(sy, g.org[1]), g.inv_cell);
+      const float lz = __fmul_rn(__fsub_rn(sz, g.org[2]), g.inv_cell);
+      const float flx = floorf(lx), fly = floorf(ly), flz = floorf(lz);
+      // queries far outside the grid (or not finite) cannot have a neighbour within the radius
+      valid = flx >= -(float)(K + 1) && flx <= (float)(g.dim[0] + K) && fly >= -(float)(K + 1) && fly <= (float)(g.dim[1] + K) &&
+              flz >= -(float)(K + 1) && flz <= (float)(g.dim[2] + K);
+      if (valid) {
+        cx = (int)flx; cy = (int)fly; cz = (int)flz;
+        fx = lx - flx; fy = ly - fly; fz = lz - flz;
+        if (cx >= 0 && cx < g.dim[0] && cy >= 0 && cy < g.dim[1] && cz >= 0 && cz < g.dim[2]) {
+          const int c = (cx * g.dim[1] + cy) * g.dim[2] + cz;
+          int best = -1, best_idx = kNoMatch;
+          nn_scan(g, __ldg(&g.cell_start[c]), __ldg(&g.cell_start[c + 1]), sx, sy, sz, bd, best, best_idx);
+          key = pack_key(bd, best_idx);
+        }
+      }
+    }
+    s_key[it][tid] = key;
+    s_qi[warp][0][lane] = cx; s_qi[warp][1][lane] = cy; s_qi[warp][2][lane] = cz;
+    s_qf[warp][0][lane] = fx; s_qf[warp][1][lane] = fy; s_qf[warp][2][lane] = fz;
+    s_qf[warp][3][lane] = sx; s_qf[warp][4][lane] = sy; s_qf[warp][5][lane] = sz;
+    // per axis, the cell offsets whose slab can still hold something as close as bd
+    int xlo = 0, xhi = 0, ylo = 0, yhi = 0;
+    if (valid) {
+      for (int o = 1; o <= K; o++) { const float a = slab_gap(o, fx, cell, slack); if (a * a > bd) break; xhi = o; }
+      for (int o = 1; o <= K; o++) { const float a = slab_gap(-o, fx, cell, slack); if (a * a > bd) break; xlo = -o; }
+      for (int o = 1; o <= K; o++) { const float a = slab_gap(o, fy, cell, slack); if (a * a > bd) break; yhi = o; }
+      for (int o = 1; o <= K; o++) { const float a = slab_gap(-o, fy, cell, slack); if (a * a > bd) break; ylo = -o; }
+    }
+    // every (query, cell column) that survives becomes one item of the warp's list; the query's own column gives two
+    // (the runs below and above the cell already scanned)
+    const int n_items = valid ? (xhi - xlo + 1) * (yhi - ylo + 1) + 1 : 0;
+    int incl = n_items;
 #pragma unroll
-  for (int i = 0; i < kAcc; i++) {
-    double v = acc[i];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-    if (lane == 0) s_part[warp][i] = v;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    if (valid) {
+      int off = incl - n_items;
+      for (int ox = xlo; ox <= xhi; ox++)
+        for (int oy = ylo; oy <= yhi; oy++) {
+          const int code = lane | ((ox + 8) << 5) | ((oy + 8) << 9);
+          s_items[warp][off++] = (unsigned short)code;
+          if (ox == 0 && oy == 0) s_items[warp][off++] = (unsigned short)(code | (1 << 13));
+        }
+    }
+    __syncwarp();
+    // the items are dealt round-robin to the lanes whatever query they belong to: the warp's work is balanced over its
+    // lanes.  Each lane re-derives the column's z run from the freshest bound of the owning query, scans it and merges
+    // the best candidate into the query's key.
+    for (int j = lane; j < total; j += 32) {
+      const int code = (int)s_items[warp][j];
+      const int q = code & 31, ox = ((code >> 5) & 15) - 8, oy = ((code >> 9) & 15) - 8;
+      const bool upper = (code >> 13) & 1;
+      const int qcx = s_qi[warp][0][q], qcy = s_qi[warp][1][q], qcz = s_qi[warp][2][q];
+      const int ix = qcx + ox, iy = qcy + oy;
+      if (ix < 0 || ix >= g.dim[0] || iy < 0 || iy >= g.dim[1]) continue;
+      unsigned long long* kp = &s_key[it][warp * 32 + q];
+      const unsigned long long cur = *(volatile unsigned long long*)kp;     // any earlier value is a valid bound
+      float bl = __uint_as_float((unsigned)(cur >> 32));
+      const float ax = slab_gap(ox, s_qf[warp][0][q], cell, slack), ay = slab_gap(oy, s_qf[warp][1][q], cell, slack);
+      const float axy2 = ax * ax + ay * ay;
+      if (axy2 > bl) continue;
+      const float qfz = s_qf[warp][2][q];
+      // z cells of one (x, y) column are contiguous in memory: one run over the cells that can still matter
+      int zhi = qcz, zlo = qcz;
+      for (int oz = 1; oz <= K; oz++) {
+        const float az = slab_gap(oz, qfz, cell, slack);
+        if (axy2 + az * az > bl) break;
+        zhi = qcz + oz;
+      }
+      for (int oz = 1; oz <= K; oz++) {
+        const float az = slab_gap(-oz, qfz, cell, slack);
+        if (axy2 + az * az > bl) break;
+        zlo = qcz - oz;
+      }
+      int a0 = max(zlo, 0), a1 = min(zhi, g.dim[2] - 1);
+      if (ox == 0 && oy == 0) {
+        if (upper) a0 = max(qcz + 1, 0); else a1 = min(qcz - 1, g.dim[2] - 1);
+      }
+      if (a0 > a1) continue;
+      const int row = (ix * g.dim[1] + iy) * g.dim[2];
+      const int s0 = __ldg(&g.cell_start[row + a0]), s1 = __ldg(&g.cell_start[row + a1 + 1]);
+      int bi = (int)(unsigned)(cur & 0xffffffffu), bs = -1;
+      nn_scan(g, s0, s1, s_qf[warp][3][q], s_qf[warp][4][q], s_qf[warp][5][q], bl, bs, bi);
+      if (bs >= 0) atomicMin(kp, pack_key(bl, bi));
+    }
+    __syncwarp();
   }
+  // phase 2: point-to-plane rows of the accepted correspondences, accumulated in two passes (15 + 14 double sums) so
+  // that the accumulators of one pass fit the register budget of the search
+  __syncwarp();
+  icp_rows<0>(S, g, &s_key[0][tid], base + tid, max_d2, s_part[warp], lane);
+  icp_rows<1>(S, g, &s_key[0][tid], base + tid, max_d2, s_part[warp], lane);
   __syncthreads();
   if (tid < kAcc) {
     double v = 0.0;
@@ -592,6 +754,7 @@ er_cloud* er_cloud_upload(int device, const float* xyz, const float* normals, si
     return nullptr;
   }
   g.pts = c->d_pts; g.nrm = c->d_nrm; g.cell_start = c->d_cell_start;
+  g.xyz_orig = c->d_xyz; g.nrm_orig = c->d_nrm_orig;
   return c;
 }
 
@@ -657,6 +820,7 @@ int er_icp_align_batch(er_cloud* const* clouds, int nclouds, const int* tgt_idx,
   ER_CUDA(cudaMalloc((void**)&d_part, sizeof(double) * part_doubles));
   ER_CUDA(cudaMalloc((void**)&d_st, sizeof(PairState) * (size_t)npairs));
   size_t co = 0, po = 0;
+  int max_rings = 1;
   for (int p = 0; p < npairs; p++) {
     const er_cloud* t = clouds[tgt_idx[p]];
     const er_cloud* s = clouds[src_idx[p]];
@@ -672,12 +836,24 @@ int er_icp_align_batch(er_cloud* const* clouds, int nclouds, const int* tgt_idx,
     if (s->n) cudaMemcpyAsync(S.cur, s->d_xyz, sizeof(float) * 3 * s->n, cudaMemcpyDeviceToDevice, ctx->stream);
     co += 3 * s->n;
     po += (size_t)S.nblocks * kAcc;
+    max_rings = std::max(max_rings, t->grid.rings);
   }
   cudaError_t e = cudaMemcpyAsync(d_st, st.data(), sizeof(PairState) * (size_t)npairs, cudaMemcpyHostToDevice, ctx->stream);
   const double max_d2 = max_dist * max_dist;
+  // the smallest float that is >= max_d2: no candidate with a larger float distance can pass `(double)d2 > max_d2`
+  float bd_init = (float)max_d2;
+  if ((double)bd_init < max_d2) bd_init = std::nextafterf(bd_init, FLT_MAX);
+  bool coop = true;
+  if (const char* ev = std::getenv("ER_ICP_COOP")) coop = std::atoi(ev) != 0;                        // experiment knob
+  if (max_rings > kMaxRings) coop = false;              // the warp's item list is sized for kMaxRings
+  int minb = 8;                                         // resident CTAs per SM the kernel is compiled for (register budget)
+  if (const char* ev = std::getenv("ER_ICP_MINB")) minb = std::atoi(ev) == 6 ? 6 : 8;              // experiment knob
   const dim3 grid((unsigned)max_blocks, (unsigned)npairs);
   for (int it = 0; it < max_iter && e == cudaSuccess; it++) {
-    icp_iter_kernel<<<grid, kThreads, 0, ctx->stream>>>(d_st, max_d2, max_iter, eps, fixed_iters);
+    if (coop && minb == 8) icp_iter_kernel<true, 8><<<grid, kThreads, 0, ctx->stream>>>(d_st, max_d2, bd_init, max_iter, eps, fixed_iters);
+    else if (coop) icp_iter_kernel<true, 6><<<grid, kThreads, 0, ctx->stream>>>(d_st, max_d2, bd_init, max_iter, eps, fixed_iters);
+    else if (minb == 8) icp_iter_kernel<false, 8><<<grid, kThreads, 0, ctx->stream>>>(d_st, max_d2, bd_init, max_iter, eps, fixed_iters);
+    else icp_iter_kernel<false, 6><<<grid, kThreads, 0, ctx->stream>>>(d_st, max_d2, bd_init, max_iter, eps, fixed_iters);
     ctx->launches++;
     e = cudaGetLastError();
   }
