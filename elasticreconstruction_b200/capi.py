@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libelastic_b200.so")
+LIB_PATH = os.environ.get("ER_B200_LIB") or os.path.join(HERE, "libelastic_b200.so")   # override: experiments only
 
 _lib = None
 

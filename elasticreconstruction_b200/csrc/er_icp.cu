@@ -38,14 +38,23 @@
 
 namespace {
 
-constexpr int kThreads = 128;
+#ifndef ER_ICP_THREADS
+#define ER_ICP_THREADS 128             // CTA size of the ICP kernels (compile-time experiment knob: 64 or 128)
+#endif
+constexpr int kThreads = ER_ICP_THREADS;
 constexpr int kPtsPerThread = 8;
 constexpr int kPtsPerCta = kThreads * kPtsPerThread;
 constexpr int kAcc = 29;               // 21 (upper ATA) + 6 (ATb) + sum d^2 + count
 constexpr int kMaxEvents = 16;
 constexpr int kMaxRings = 2;           // cooperative search: at most (2*2+1)^2 + 1 = 26 cell-column items per query
 constexpr int kMaxItems = 32 * ((2 * kMaxRings + 1) * (2 * kMaxRings + 1) + 1);
+constexpr int kRunCap = 64;            // per-warp list of point runs waiting to be scanned (drained at 32)
 constexpr int kNoMatch = 0x7fffffff;
+
+// the 25 cell columns around a query's own, nearest first (cooperative search, rings <= 2)
+__constant__ signed char kColumnOrder[25][2] = {
+    {0, 0},  {-1, 0}, {1, 0},  {0, -1}, {0, 1},  {-1, -1}, {-1, 1}, {1, -1}, {1, 1},  {-2, 0}, {2, 0},  {0, -2}, {0, 2},
+    {-2, -1}, {-2, 1}, {2, -1}, {2, 1}, {-1, -2}, {-1, 2}, {1, -2}, {1, 2},  {-2, -2}, {-2, 2}, {2, -2}, {2, 2}};
 
 struct GridDev {
   const float4* pts;      // sorted by cell: x, y, z, original index (int bits)
@@ -79,6 +88,30 @@ struct PairState {
 // its lower distance bound (computed from the query's position inside its cell, minus a slack that covers the
 // float rounding of the cell assignment) does not exceed the best distance so far -- so a converged pair scans
 // a handful of candidates instead of the full neighbourhood, with the same result as the exhaustive scan.
+// A candidate as one 64-bit key: float bits of d^2 (non-negative, so they order like the values) << 32 | original
+// index.  The smallest key is the nearest neighbour with ties going to the smallest original index; a NaN distance
+// has larger bits than any finite one and never wins.
+__device__ __forceinline__ unsigned long long pack_key(float d2, int idx) {
+  return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)idx;
+}
+
+__device__ __forceinline__ unsigned long long nn_key(const float4 p, float qx, float qy, float qz) {
+  const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
+  return pack_key(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)), __float_as_int(p.w));
+}
+
+// key = min(key, keys of the candidates s0..s1-1); four loads in flight (slots past the end re-read the last point)
+__device__ __forceinline__ void nn_scan_key(const GridDev& g, int s0, int s1, float qx, float qy, float qz, unsigned long long& key) {
+  const int last = s1 - 1;
+  for (int s = s0; s < s1; s += 4) {
+    const float4 p0 = __ldg(&g.pts[s]);
+    const float4 p1 = __ldg(&g.pts[min(s + 1, last)]);
+    const float4 p2 = __ldg(&g.pts[min(s + 2, last)]);
+    const float4 p3 = __ldg(&g.pts[min(s + 3, last)]);
+    key = min(min(key, nn_key(p0, qx, qy, qz)), min(nn_key(p1, qx, qy, qz), min(nn_key(p2, qx, qy, qz), nn_key(p3, qx, qy, qz))));
+  }
+}
+
 __device__ __forceinline__ void nn_consider(const float4 p, int s, float qx, float qy, float qz, float& bd, int& best, int& best_idx) {
   const float dx = __fsub_rn(qx, p.x), dy = __fsub_rn(qy, p.y), dz = __fsub_rn(qz, p.z);
   const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
@@ -212,16 +245,14 @@ __device__ bool solve6(double* A, double* b, double* x) {
 //                 the cell columns (x, y offsets) that can still hold something as close as bd -- usually one to
 //                 four -- as items (lane, ox, oy) in a per-warp list in shared memory.  The items are then dealt
 //                 round-robin to the lanes regardless of the query they belong to: a lane derives the column's run of
-//                 z cells from the owning query's freshest bound, scans it and merges the best candidate into the
-//                 query's 64-bit key (float bits of d^2 << 32 | original index) with atomicMin in shared memory.
-//                 The warp's work is thereby balanced over its lanes whatever the spread between its queries.
+//                 z cells from the owning query's freshest bound (most items are pruned here); the surviving point
+//                 runs are compacted into a second list, dealt round-robin again and scanned, the best candidate of
+//                 a run merged into the query's 64-bit key (float bits of d^2 << 32 | original index) with atomicMin
+//                 in shared memory.  The warp's work is thereby balanced over its lanes whatever the spread between
+//                 its queries.
 // A match is kept as that 64-bit key; kNoMatch in the low word means none.  Candidates with d^2 above bd_init (the
 // float just above max_dist^2) can never be kept, so the search starts from that bound.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ unsigned long long pack_key(float d2, int idx) {
-  return ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned)idx;
-}
-
 // offset bound: distance from a query at fraction f of its cell to the slab `o` cells away (0 for its own slab)
 __device__ __forceinline__ float slab_gap(int o, float f, float cell, float slack) {
   return fmaxf(0.0f, (o > 0 ? ((float)o - f) : (o < 0 ? (f - (float)(o + 1)) : 0.0f)) * cell - slack);
@@ -282,7 +313,7 @@ __device__ __forceinline__ void icp_rows(const PairState& S, const GridDev& g, c
 }
 
 template <bool COOP, int MINB>
-__global__ void __launch_bounds__(kThreads, MINB) icp_iter_kernel(PairState* states, double max_d2, float bd_init, int max_iter,
+__global__ void __launch_bounds__(kThreads, MINB * 128 / kThreads) icp_iter_kernel(PairState* states, double max_d2, float bd_init, int max_iter,
                                                             double eps, int fixed_iters) {
   PairState& S = states[blockIdx.y];
   if (blockIdx.x >= S.nblocks || S.done) return;
@@ -298,6 +329,7 @@ __global__ void __launch_bounds__(kThreads, MINB) icp_iter_kernel(PairState* sta
   // phase 1: move the points and search (the double accumulators are not live yet: lower register pressure)
   __shared__ unsigned long long s_key[kPtsPerThread][kThreads];
   __shared__ unsigned short s_items[COOP ? kThreads / 32 : 1][COOP ? kMaxItems : 1];   // lane | ox+8 | oy+8 | upper
+  __shared__ int2 s_runs[COOP ? kThreads / 32 : 1][COOP ? kRunCap : 1];                      // start, length << 5 | lane
   __shared__ int s_qi[COOP ? kThreads / 32 : 1][3][32];
   __shared__ float s_qf[COOP ? kThreads / 32 : 1][6][32];
 #pragma unroll 1
@@ -342,9 +374,8 @@ __global__ void __launch_bounds__(kThreads, MINB) icp_iter_kernel(PairState* sta
         fx = lx - flx; fy = ly - fly; fz = lz - flz;
         if (cx >= 0 && cx < g.dim[0] && cy >= 0 && cy < g.dim[1] && cz >= 0 && cz < g.dim[2]) {
           const int c = (cx * g.dim[1] + cy) * g.dim[2] + cz;
-          int best = -1, best_idx = kNoMatch;
-          nn_scan(g, __ldg(&g.cell_start[c]), __ldg(&g.cell_start[c + 1]), sx, sy, sz, bd, best, best_idx);
-          key = pack_key(bd, best_idx);
+          nn_scan_key(g, __ldg(&g.cell_start[c]), __ldg(&g.cell_start[c + 1]), sx, sy, sz, key);
+          bd = __uint_as_float((unsigned)(key >> 32));
         }
       }
     }
@@ -361,63 +392,95 @@ __global__ void __launch_bounds__(kThreads, MINB) icp_iter_kernel(PairState* sta
       for (int o = 1; o <= K; o++) { const float a = slab_gap(-o, fy, cell, slack); if (a * a > bd) break; ylo = -o; }
     }
     // every (query, cell column) that survives becomes one item of the warp's list; the query's own column gives two
-    // (the runs below and above the cell already scanned)
-    const int n_items = valid ? (xhi - xlo + 1) * (yhi - ylo + 1) + 1 : 0;
-    int incl = n_items;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += t; }
-    const int total = __shfl_sync(0xffffffffu, incl, 31);
-    if (valid) {
-      int off = incl - n_items;
-      for (int ox = xlo; ox <= xhi; ox++)
-        for (int oy = ylo; oy <= yhi; oy++) {
-          const int code = lane | ((ox + 8) << 5) | ((oy + 8) << 9);
-          s_items[warp][off++] = (unsigned short)code;
-          if (ox == 0 && oy == 0) s_items[warp][off++] = (unsigned short)(code | (1 << 13));
+    // (the runs below and above the cell already scanned).  The list is ordered by the column's distance from the
+    // query's column, nearest first for all queries of the warp, so that the bounds tighten before the far columns
+    // are looked at.
+    const unsigned lt_mask = (1u << lane) - 1u;
+    int total = 0;
+    {
+      const unsigned bal = __ballot_sync(0xffffffffu, valid);
+      if (valid) {
+        const int code = lane | (8 << 5) | (8 << 9), at = 2 * __popc(bal & lt_mask);
+        s_items[warp][at] = (unsigned short)code;
+        s_items[warp][at + 1] = (unsigned short)(code | (1 << 13));
+      }
+      total = 2 * __popc(bal);
+    }
+    const int reach = __reduce_max_sync(0xffffffffu, max(max(-xlo, xhi), max(-ylo, yhi)));   // 0 for idle lanes
+    const int ncol = reach == 0 ? 1 : (reach == 1 ? 9 : 25);
+    for (int t = 1; t < ncol; t++) {
+      const int ox = kColumnOrder[t][0], oy = kColumnOrder[t][1];
+      const bool in = valid && ox >= xlo && ox <= xhi && oy >= ylo && oy <= yhi;
+      const unsigned bal = __ballot_sync(0xffffffffu, in);
+      if (in) s_items[warp][total + __popc(bal & lt_mask)] = (unsigned short)(lane | ((ox + 8) << 5) | ((oy + 8) << 9));
+      total += __popc(bal);
+    }
+    __syncwarp();
+    // The items are dealt round-robin to the lanes whatever query they belong to.  First every lane derives its
+    // column's run of z cells from the freshest bound of the owning query (most items end here) and the surviving
+    // point runs are compacted into a second list; then the runs are dealt round-robin and scanned, each run's best
+    // candidate merged into its query's key.  Both steps keep most lanes of the warp busy.
+    int rn = 0;                                                   // runs waiting in s_runs (warp-uniform)
+    auto drain = [&]() {
+      __syncwarp();
+      for (int r = lane; r < rn; r += 32) {
+        const int2 run = s_runs[warp][r];
+        const int q = run.y & 31;
+        unsigned long long* kp = &s_key[it][warp * 32 + q];
+        const unsigned long long cur = *(volatile unsigned long long*)kp;   // any earlier value is a valid bound
+        unsigned long long best = cur;
+        nn_scan_key(g, run.x, run.x + (run.y >> 5), s_qf[warp][3][q], s_qf[warp][4][q], s_qf[warp][5][q], best);
+        if (best < cur) atomicMin(kp, best);
+      }
+      __syncwarp();
+      rn = 0;
+    };
+    for (int j0 = 0; j0 < total; j0 += 32) {
+      const int j = j0 + lane;
+      int s0 = 0, s1 = 0, q = 0;
+      do {
+        if (j >= total) break;
+        const int code = (int)s_items[warp][j];
+        q = code & 31;
+        const int ox = ((code >> 5) & 15) - 8, oy = ((code >> 9) & 15) - 8;
+        const bool upper = (code >> 13) & 1;
+        const int qcx = s_qi[warp][0][q], qcy = s_qi[warp][1][q], qcz = s_qi[warp][2][q];
+        const int ix = qcx + ox, iy = qcy + oy;
+        if (ix < 0 || ix >= g.dim[0] || iy < 0 || iy >= g.dim[1]) break;
+        const unsigned long long cur = *(volatile unsigned long long*)&s_key[it][warp * 32 + q];
+        const float bl = __uint_as_float((unsigned)(cur >> 32));
+        const float ax = slab_gap(ox, s_qf[warp][0][q], cell, slack), ay = slab_gap(oy, s_qf[warp][1][q], cell, slack);
+        const float axy2 = ax * ax + ay * ay;
+        if (axy2 > bl) break;
+        const float qfz = s_qf[warp][2][q];
+        // z cells of one (x, y) column are contiguous in memory: one run over the cells that can still matter
+        int zhi = qcz, zlo = qcz;
+        for (int oz = 1; oz <= K; oz++) {
+          const float az = slab_gap(oz, qfz, cell, slack);
+          if (axy2 + az * az > bl) break;
+          zhi = qcz + oz;
         }
+        for (int oz = 1; oz <= K; oz++) {
+          const float az = slab_gap(-oz, qfz, cell, slack);
+          if (axy2 + az * az > bl) break;
+          zlo = qcz - oz;
+        }
+        int a0 = max(zlo, 0), a1 = min(zhi, g.dim[2] - 1);
+        if (ox == 0 && oy == 0) {
+          if (upper) a0 = max(qcz + 1, 0); else a1 = min(qcz - 1, g.dim[2] - 1);
+        }
+        if (a0 > a1) break;
+        const int row = (ix * g.dim[1] + iy) * g.dim[2];
+        s0 = __ldg(&g.cell_start[row + a0]);
+        s1 = __ldg(&g.cell_start[row + a1 + 1]);
+      } while (false);
+      const bool has = s1 > s0;
+      const unsigned bal = __ballot_sync(0xffffffffu, has);
+      if (has) s_runs[warp][rn + __popc(bal & lt_mask)] = make_int2(s0, ((s1 - s0) << 5) | q);
+      rn += __popc(bal);
+      if (rn >= 32) drain();                                      // a full round of runs: scan now, tighten the bounds
     }
-    __syncwarp();
-    // the items are dealt round-robin to the lanes whatever query they belong to: the warp's work is balanced over its
-    // lanes.  Each lane re-derives the column's z run from the freshest bound of the owning query, scans it and merges
-    // the best candidate into the query's key.
-    for (int j = lane; j < total; j += 32) {
-      const int code = (int)s_items[warp][j];
-      const int q = code & 31, ox = ((code >> 5) & 15) - 8, oy = ((code >> 9) & 15) - 8;
-      const bool upper = (code >> 13) & 1;
-      const int qcx = s_qi[warp][0][q], qcy = s_qi[warp][1][q], qcz = s_qi[warp][2][q];
-      const int ix = qcx + ox, iy = qcy + oy;
-      if (ix < 0 || ix >= g.dim[0] || iy < 0 || iy >= g.dim[1]) continue;
-      unsigned long long* kp = &s_key[it][warp * 32 + q];
-      const unsigned long long cur = *(volatile unsigned long long*)kp;     // any earlier value is a valid bound
-      float bl = __uint_as_float((unsigned)(cur >> 32));
-      const float ax = slab_gap(ox, s_qf[warp][0][q], cell, slack), ay = slab_gap(oy, s_qf[warp][1][q], cell, slack);
-      const float axy2 = ax * ax + ay * ay;
-      if (axy2 > bl) continue;
-      const float qfz = s_qf[warp][2][q];
-      // z cells of one (x, y) column are contiguous in memory: one run over the cells that can still matter
-      int zhi = qcz, zlo = qcz;
-      for (int oz = 1; oz <= K; oz++) {
-        const float az = slab_gap(oz, qfz, cell, slack);
-        if (axy2 + az * az > bl) break;
-        zhi = qcz + oz;
-      }
-      for (int oz = 1; oz <= K; oz++) {
-        const float az = slab_gap(-oz, qfz, cell, slack);
-        if (axy2 + az * az > bl) break;
-        zlo = qcz - oz;
-      }
-      int a0 = max(zlo, 0), a1 = min(zhi, g.dim[2] - 1);
-      if (ox == 0 && oy == 0) {
-        if (upper) a0 = max(qcz + 1, 0); else a1 = min(qcz - 1, g.dim[2] - 1);
-      }
-      if (a0 > a1) continue;
-      const int row = (ix * g.dim[1] + iy) * g.dim[2];
-      const int s0 = __ldg(&g.cell_start[row + a0]), s1 = __ldg(&g.cell_start[row + a1 + 1]);
-      int bi = (int)(unsigned)(cur & 0xffffffffu), bs = -1;
-      nn_scan(g, s0, s1, s_qf[warp][3][q], s_qf[warp][4][q], s_qf[warp][5][q], bl, bs, bi);
-      if (bs >= 0) atomicMin(kp, pack_key(bl, bi));
-    }
-    __syncwarp();
+    drain();
   }
   // phase 2: point-to-plane rows of the accepted correspondences, accumulated in two passes (15 + 14 double sums) so
   // that the accumulators of one pass fit the register budget of the search
