@@ -42,7 +42,13 @@ namespace {
 #define ER_ICP_THREADS 128             // CTA size of the ICP kernels (compile-time experiment knob: 64 or 128)
 #endif
 constexpr int kThreads = ER_ICP_THREADS;
-constexpr int kPtsPerThread = 8;
+#ifndef ER_ICP_PTS
+#define ER_ICP_PTS 8                   // source points per thread (compile-time experiment knob)
+#endif
+#ifndef ER_ICP_SCANW
+#define ER_ICP_SCANW 4                 // candidate loads in flight per scan step (4 or 8)
+#endif
+constexpr int kPtsPerThread = ER_ICP_PTS;
 constexpr int kPtsPerCta = kThreads * kPtsPerThread;
 constexpr int kAcc = 29;               // 21 (upper ATA) + 6 (ATb) + sum d^2 + count
 constexpr int kMaxEvents = 16;
@@ -103,12 +109,22 @@ __device__ __forceinline__ unsigned long long nn_key(const float4 p, float qx, f
 // key = min(key, keys of the candidates s0..s1-1); four loads in flight (slots past the end re-read the last point)
 __device__ __forceinline__ void nn_scan_key(const GridDev& g, int s0, int s1, float qx, float qy, float qz, unsigned long long& key) {
   const int last = s1 - 1;
-  for (int s = s0; s < s1; s += 4) {
+  for (int s = s0; s < s1; s += ER_ICP_SCANW) {
     const float4 p0 = __ldg(&g.pts[s]);
     const float4 p1 = __ldg(&g.pts[min(s + 1, last)]);
     const float4 p2 = __ldg(&g.pts[min(s + 2, last)]);
     const float4 p3 = __ldg(&g.pts[min(s + 3, last)]);
+#if ER_ICP_SCANW == 8
+    const float4 p4 = __ldg(&g.pts[min(s + 4, last)]);
+    const float4 p5 = __ldg(&g.pts[min(s + 5, last)]);
+    const float4 p6 = __ldg(&g.pts[min(s + 6, last)]);
+    const float4 p7 = __ldg(&g.pts[min(s + 7, last)]);
+#endif
     key = min(min(key, nn_key(p0, qx, qy, qz)), min(nn_key(p1, qx, qy, qz), min(nn_key(p2, qx, qy, qz), nn_key(p3, qx, qy, qz))));
+#if ER_ICP_SCANW == 8
+    if (s + 4 <= last)
+      key = min(min(key, nn_key(p4, qx, qy, qz)), min(nn_key(p5, qx, qy, qz), min(nn_key(p6, qx, qy, qz), nn_key(p7, qx, qy, qz))));
+#endif
   }
 }
 

@@ -72,3 +72,17 @@ def test_no_cpu_fallback_without_device():
     import numpy as np
     with pytest.raises(capi.ElasticError, match="no CPU path|not available"):
         capi.Cloud(np.zeros((4, 3), np.float32), np.zeros((4, 3), np.float32))
+
+
+def test_committed_traffic_table_is_usable():
+    """bench.py reports roofline.traffic from profiles/traffic.json (DRAM bytes of one ncu --set full capture);
+    a malformed table would silently turn that into null."""
+    import importlib.util
+    import json
+    t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    for k in ("integrate_kernel", "icp_iter_kernel"):
+        assert isinstance(t[k]["dram_bytes_per_launch"], float) and isinstance(t[k]["units_per_launch"], float)
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.load_traffic("integrate_kernel") > 1e6

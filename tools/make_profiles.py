@@ -54,7 +54,7 @@ def main():
                 for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                     f.write("%-40s launches=%5d total_us=%12.1f avg_us=%10.1f share=%5.1f%%\n" % (k[:40], n, t, t / n, 100 * t / tot))
             continue
-        hdr, units, data = raw_rows(path)
+        hdr, unit_row, data = raw_rows(path)
         out = os.path.join(ROOT, "profiles", "%s_%s.txt" % (rnd, name))
         import io
         import contextlib
@@ -66,7 +66,7 @@ def main():
             f.write(buf.getvalue())
         r = data[0]
         g = lambda m: float(r[hdr.index(m)].replace(",", ""))   # noqa: E731
-        u = lambda m: units[hdr.index(m)]                          # noqa: E731
+        u = lambda m: unit_row[hdr.index(m)]                         # noqa: E731
 
         def to_bytes(m):
             scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u(m)]
