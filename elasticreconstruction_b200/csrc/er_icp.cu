@@ -22,6 +22,7 @@
 // order (per-thread -> warp shuffle tree -> per-CTA partial -> last CTA sums partials by index), so results are
 // reproducible run to run.
 #include <cuda_runtime.h>
+#include <cub/device/device_scan.cuh>
 
 #include <algorithm>
 #include <cfloat>
@@ -719,6 +720,41 @@ __global__ void __launch_bounds__(kThreads) compact_kernel(const int* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
+// Grid build (once per fragment, on the device): cell of every point -> counting sort by cell.
+//   grid_count_kernel    cid[i] = cell of point i; histogram into A[cell + 2]
+//   (inclusive scan of A in place: A[c + 1] = number of points in the cells before c)
+//   grid_scatter_kernel  pos = atomicAdd(&A[cid + 1], 1): the cursor of cell c starts at its first slot and ends at
+//                        the first slot of cell c + 1, so after the scatter A[0..ncell] is the cell_start table
+// The order of the points inside a cell depends on the atomics; the search results do not (nearest neighbour with
+// ties to the smallest ORIGINAL index, which travels in pts[].w).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int grid_cell_axis(float v, float org, float inv_cell, int dim) {
+  const int i = __float2int_rd(__fmul_rn(__fsub_rn(v, org), inv_cell));       // floor; NaN -> 0
+  return min(max(i, 0), dim - 1);
+}
+
+__global__ void __launch_bounds__(256) grid_count_kernel(GridDev g, const float* __restrict__ xyz, int n, int* __restrict__ cid,
+                                                         int* __restrict__ A) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int c = (grid_cell_axis(xyz[3 * (size_t)i], g.org[0], g.inv_cell, g.dim[0]) * g.dim[1] +
+                 grid_cell_axis(xyz[3 * (size_t)i + 1], g.org[1], g.inv_cell, g.dim[1])) * g.dim[2] +
+                grid_cell_axis(xyz[3 * (size_t)i + 2], g.org[2], g.inv_cell, g.dim[2]);
+  cid[i] = c;
+  atomicAdd(&A[c + 2], 1);
+}
+
+__global__ void __launch_bounds__(256) grid_scatter_kernel(const float* __restrict__ xyz, const float* __restrict__ nrm, int n,
+                                                           const int* __restrict__ cid, int* __restrict__ A,
+                                                           float4* __restrict__ pts, float4* __restrict__ snrm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int pos = atomicAdd(&A[cid[i] + 1], 1);
+  pts[pos] = make_float4(xyz[3 * (size_t)i], xyz[3 * (size_t)i + 1], xyz[3 * (size_t)i + 2], __int_as_float(i));
+  snrm[pos] = make_float4(nrm[3 * (size_t)i], nrm[3 * (size_t)i + 1], nrm[3 * (size_t)i + 2], 0.0f);
+}
+
+// ---------------------------------------------------------------------------------------------
 struct IcpCtx {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -746,6 +782,7 @@ IcpCtx* get_ctx(int device) {
 struct er_cloud {
   int device = 0;
   size_t n = 0;
+  void* d_block = nullptr;     // one allocation holding everything below
   float4* d_pts = nullptr;
   float4* d_nrm = nullptr;
   int* d_cell_start = nullptr;
@@ -769,7 +806,7 @@ er_cloud* er_cloud_upload(int device, const float* xyz, const float* normals, si
   if (!c) return nullptr;
   c->device = device;
   c->n = n;
-  // ---- uniform grid over the bounding box (host side; done once per fragment, outside the iteration loop)
+  // ---- uniform grid over the bounding box (the box on the host, the counting sort on the device; once per fragment)
   float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   for (size_t i = 0; i < n; i++)
     for (int a = 0; a < 3; a++) {
@@ -777,7 +814,8 @@ er_cloud* er_cloud_upload(int device, const float* xyz, const float* normals, si
       if (v < lo[a]) lo[a] = v;
       if (v > hi[a]) hi[a] = v;
     }
-  if (n == 0) for (int a = 0; a < 3; a++) lo[a] = hi[a] = 0.f;
+  for (int a = 0; a < 3; a++)
+    if (n == 0 || !(lo[a] <= hi[a])) lo[a] = hi[a] = 0.f;       // empty cloud, or no finite coordinate on this axis
   // cells of half the admissible radius (a hair more), searched two rings deep: fewer candidates per cell
   int rings = 2;
   if (const char* e = std::getenv("ER_ICP_RINGS")) rings = std::max(1, std::min(6, std::atoi(e)));   // experiment knob
@@ -796,51 +834,54 @@ er_cloud* er_cloud_upload(int device, const float* xyz, const float* normals, si
   g.rings = rings;
   for (int a = 0; a < 3; a++) { g.org[a] = lo[a]; g.dim[a] = dim[a]; }
   const size_t ncell = (size_t)dim[0] * dim[1] * dim[2];
-  std::vector<int> cell_start(ncell + 1, 0), cid(n);
-  auto cell_of = [&](float v, int a) {
-    int i = (int)std::floor((v - g.org[a]) * g.inv_cell);
-    return std::min(std::max(i, 0), dim[a] - 1);
-  };
-  for (size_t i = 0; i < n; i++) {
-    cid[i] = (cell_of(xyz[3 * i], 0) * dim[1] + cell_of(xyz[3 * i + 1], 1)) * dim[2] + cell_of(xyz[3 * i + 2], 2);
-    cell_start[cid[i] + 1]++;
-  }
-  for (size_t k = 0; k < ncell; k++) cell_start[k + 1] += cell_start[k];
-  std::vector<int> fill(cell_start.begin(), cell_start.end() - 1);
-  std::vector<float4> pts(n ? n : 1), nrm(n ? n : 1);
-  for (size_t i = 0; i < n; i++) {
-    const int pos = fill[cid[i]]++;
-    int idx = (int)i;
-    float w;
-    std::memcpy(&w, &idx, sizeof w);
-    pts[pos] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], w);
-    nrm[pos] = make_float4(normals[3 * i], normals[3 * i + 1], normals[3 * i + 2], 0.f);
-  }
+  // one device allocation: sorted points and normals, the original-order copies, the cell table (+1 cursor slot),
+  // and the build's scratch (cell of every point, scan workspace)
+  IcpCtx* ctx = get_ctx(device);
   cudaError_t e = cudaSetDevice(device);
-  auto up = [&](void** dptr, const void* src, size_t bytes) {
-    if (e != cudaSuccess) return;
-    e = cudaMalloc(dptr, bytes ? bytes : 16);
-    if (e == cudaSuccess && bytes) e = cudaMemcpy(*dptr, src, bytes, cudaMemcpyHostToDevice);
-  };
-  up((void**)&c->d_pts, pts.data(), sizeof(float4) * n);
-  up((void**)&c->d_nrm, nrm.data(), sizeof(float4) * n);
-  up((void**)&c->d_cell_start, cell_start.data(), sizeof(int) * (ncell + 1));
-  up((void**)&c->d_xyz, xyz, sizeof(float) * 3 * n);
-  up((void**)&c->d_nrm_orig, normals, sizeof(float) * 3 * n);
+  size_t scan_bytes = 0;
+  if (e == cudaSuccess) e = cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (int*)nullptr, (int*)nullptr, (int)(ncell + 2), ctx->stream);
+  auto up256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
+  const size_t o_pts = 0, o_nrm = o_pts + up256(sizeof(float4) * n), o_xyz = o_nrm + up256(sizeof(float4) * n),
+               o_no = o_xyz + up256(sizeof(float) * 3 * n), o_A = o_no + up256(sizeof(float) * 3 * n),
+               o_cid = o_A + up256(sizeof(int) * (ncell + 2)), o_scan = o_cid + up256(sizeof(int) * n),
+               total = o_scan + up256(scan_bytes) + 256;
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_block, total);
+  if (e == cudaSuccess) {
+    char* base = (char*)c->d_block;
+    c->d_pts = (float4*)(base + o_pts); c->d_nrm = (float4*)(base + o_nrm);
+    c->d_xyz = (float*)(base + o_xyz); c->d_nrm_orig = (float*)(base + o_no);
+    c->d_cell_start = (int*)(base + o_A);
+    int* d_cid = (int*)(base + o_cid);
+    void* d_scan = base + o_scan;
+    g.pts = c->d_pts; g.nrm = c->d_nrm; g.cell_start = c->d_cell_start;
+    g.xyz_orig = c->d_xyz; g.nrm_orig = c->d_nrm_orig;
+    if (n) e = cudaMemcpyAsync(c->d_xyz, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(c->d_nrm_orig, normals, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_cell_start, 0, sizeof(int) * (ncell + 2), ctx->stream);
+    if (e == cudaSuccess && n) {
+      const int nb = (int)((n + 255) / 256);
+      grid_count_kernel<<<nb, 256, 0, ctx->stream>>>(g, c->d_xyz, (int)n, d_cid, c->d_cell_start);
+      e = cub::DeviceScan::InclusiveSum(d_scan, scan_bytes, c->d_cell_start, c->d_cell_start, (int)(ncell + 2), ctx->stream);
+      if (e == cudaSuccess) {
+        grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(c->d_xyz, c->d_nrm_orig, (int)n, d_cid, c->d_cell_start, c->d_pts, c->d_nrm);
+        e = cudaGetLastError();
+      }
+    }
+    // the caller's buffers may be reused after return, and build errors belong to this call
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  }
   if (e != cudaSuccess) {
     er::set_error("er_cloud_upload: %s", cudaGetErrorString(e));
     er_cloud_free(c);
     return nullptr;
   }
-  g.pts = c->d_pts; g.nrm = c->d_nrm; g.cell_start = c->d_cell_start;
-  g.xyz_orig = c->d_xyz; g.nrm_orig = c->d_nrm_orig;
   return c;
 }
 
 void er_cloud_free(er_cloud* c) {
   if (!c) return;
   cudaSetDevice(c->device);
-  cudaFree(c->d_pts); cudaFree(c->d_nrm); cudaFree(c->d_cell_start); cudaFree(c->d_xyz); cudaFree(c->d_nrm_orig);
+  cudaFree(c->d_block);
   delete c;
 }
 
@@ -869,10 +910,30 @@ int er_icp_count_inliers(er_cloud* tgt, er_cloud* src, const double T[16], doubl
   return ER_OK;
 }
 
+static int align_chunk(er_cloud* const* clouds, int nclouds, const int* tgt_idx, const int* src_idx, int npairs,
+                       const double* Tinit, double max_dist, int max_iter, double eps, int fixed_iters, double* Tout,
+                       int* iters, double* fitness);
+
 int er_icp_align_batch(er_cloud* const* clouds, int nclouds, const int* tgt_idx, const int* src_idx, int npairs,
                        const double* Tinit, double max_dist, int max_iter, double eps, int fixed_iters, double* Tout,
                        int* iters, double* fitness) {
   ER_ARG(clouds && nclouds > 0 && tgt_idx && src_idx && npairs >= 0 && Tinit && Tout && max_iter >= 1, "align_batch: bad arguments");
+  // every pair in flight owns a working copy of its source cloud (12 B per point); ER_ICP_CHUNK bounds that memory
+  // by aligning the list in chunks (each chunk pays its own allocations and a synchronisation)
+  int chunk = npairs > 0 ? npairs : 1;     // measured: 5 chunks of 256 pairs cost 620 ms against 406 ms for one batch of 1225
+  if (const char* ev = std::getenv("ER_ICP_CHUNK")) chunk = std::max(1, std::atoi(ev));             // experiment knob
+  for (int p0 = 0; p0 < npairs; p0 += chunk) {
+    const int n = std::min(chunk, npairs - p0);
+    const int rc = align_chunk(clouds, nclouds, tgt_idx + p0, src_idx + p0, n, Tinit + 16 * (size_t)p0, max_dist, max_iter, eps,
+                               fixed_iters, Tout + 16 * (size_t)p0, iters ? iters + p0 : nullptr, fitness ? fitness + p0 : nullptr);
+    if (rc != ER_OK) return rc;
+  }
+  return ER_OK;
+}
+
+static int align_chunk(er_cloud* const* clouds, int nclouds, const int* tgt_idx, const int* src_idx, int npairs,
+                       const double* Tinit, double max_dist, int max_iter, double eps, int fixed_iters, double* Tout,
+                       int* iters, double* fitness) {
   if (npairs == 0) return ER_OK;
   const int device = clouds[0]->device;
   IcpCtx* ctx = get_ctx(device);
