@@ -362,17 +362,18 @@ def main():
            "d2h_bytes_per_step": 4 + 32, "timing": "wall clock around the C-ABI calls, barrier+sync both sides"}
     del vol3
 
-    # ---------------- cpu baseline (rank 0, N = 1 only), ICP secondary metric
-    cpu = None
-    if rank == 0 and world == 1 and args.cpu_frames > 0:
-        cpu = cpu_baseline_leg(poses, args.cpu_frames)
+    # ---------------- ICP secondary metric, then the cpu baseline (rank 0, N = 1 only; last, so that no GPU leg starts
+    # from the idle clocks the GPU drops to while the host is busy)
     icp = None
     if not args.no_icp:
         del vol, d_frames, pinned
         torch.cuda.empty_cache()
         from elasticreconstruction_b200 import icp_bench
         icp = icp_bench.run(local, rank, world, barrier, peak_gbs=peak, num_fragments=args.icp_fragments,
-                            points=args.icp_points)
+                            points=args.icp_points, clock_sampler=ClockSampler)
+    cpu = None
+    if rank == 0 and world == 1 and args.cpu_frames > 0:
+        cpu = cpu_baseline_leg(poses, args.cpu_frames)
 
     if rank == 0:
         line = {
