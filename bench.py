@@ -4,8 +4,8 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
 
 Metric (BASELINE.json): depth frames/s integrated into a 512^3 TSDF (configs[1]: 1000 synthetic 640x480
-frames, rigid trajectory, 512^3 = 8^3 blocks of 64^3 voxels @ 3/512 m, one B200).  A "step" is one batch of
---frames-per-step consecutive frames of that sequence handed to the library in one call.
+frames, rigid trajectory, 512^3 = 8^3 blocks of 64^3 voxels @ 3/512 m, one B200).  A "step" is one pass over
+that sequence: --frames-per-step (default: all 1000) consecutive frames handed to the library in one call.
 
   value       frames/s with the frames already resident in HBM (er_tsdf_integrate_device)
   e2e         frames/s through the C-ABI with HOST buffers: pinned host frames -> er_tsdf_integrate_batch
@@ -221,7 +221,8 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--frames-per-step", type=int, default=250)
+    ap.add_argument("--frames-per-step", type=int, default=SEQ_FRAMES,
+                    help="frames handed to the library per call; must divide the 1000-frame sequence")
     ap.add_argument("--ref-frames-per-step", type=int, default=8)
     ap.add_argument("--cpu-frames", type=int, default=120, help="frames timed for cpu_baseline (0 = skip)")
     ap.add_argument("--fusion", type=int, default=32, help="frames per fused launch triple (1..32)")
