@@ -50,6 +50,8 @@ def lib():
         L.oracle_scale_depth.argtypes = [C.c_void_p, u16p, fp]
         L.oracle_tsdf_integrate.restype = C.c_int
         L.oracle_tsdf_integrate.argtypes = [C.c_void_p, u16p, dp]
+        L.oracle_tsdf_last_touched.restype = C.c_int
+        L.oracle_tsdf_last_touched.argtypes = [C.c_void_p, C.POINTER(C.c_int)]
         L.oracle_tsdf_last_updated_voxels.restype = C.c_longlong
         L.oracle_tsdf_last_updated_voxels.argtypes = [C.c_void_p]
         L.oracle_tsdf_num_blocks.restype = C.c_int
@@ -148,6 +150,13 @@ class OracleTSDF:
         depth = np.ascontiguousarray(depth, dtype=np.uint16)
         T = np.ascontiguousarray(T, dtype=np.float64).reshape(16)
         return lib().oracle_tsdf_integrate(self._h, _u16p(depth), _dp(T))
+
+    def last_touched(self) -> np.ndarray:
+        """Keys of the blocks the last integrate() touched (== its IntegrateVolumeUnit calls), first-touch order."""
+        n = lib().oracle_tsdf_last_touched(self._h, None)
+        keys = np.zeros(max(n, 1), dtype=np.int32)
+        lib().oracle_tsdf_last_touched(self._h, keys.ctypes.data_as(C.POINTER(C.c_int)))
+        return keys[:n]
 
     def last_updated_voxels(self) -> int:
         return int(lib().oracle_tsdf_last_updated_voxels(self._h))

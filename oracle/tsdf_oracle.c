@@ -48,6 +48,7 @@ typedef struct {
   /* statistics of the last integrate call (for the roofline's N_updated) */
   long long last_updated_voxels;
   int last_touched_blocks;
+  int *last_touched_keys;          /* keys of the blocks the last frame touched, in first-touch order */
 } oracle_tsdf;
 
 /* ------------------------------------------------------------------ small double 4x4 helpers */
@@ -179,7 +180,7 @@ oracle_tsdf *oracle_tsdf_create(int cols, int rows) {
 void oracle_tsdf_destroy(oracle_tsdf *o) {
   if (!o) return;
   for (int i = 0; i < o->nblocks; i++) { free(o->blocks[i].sdf); free(o->blocks[i].weight); }
-  free(o->blocks); free(o->table); free(o->scaled); free(o);
+  free(o->blocks); free(o->table); free(o->scaled); free(o->last_touched_keys); free(o);
 }
 
 void oracle_tsdf_set_camera(oracle_tsdf *o, float fx, float fy, float cx, float cy, float integration_trunc) {
@@ -338,7 +339,8 @@ int oracle_tsdf_integrate_scaled(oracle_tsdf *o, const uint16_t *depth, const fl
       }
     }
   }
-  free(touched);
+  free(o->last_touched_keys);
+  o->last_touched_keys = touched;
   o->last_updated_voxels = updated;
   o->last_touched_blocks = ntouched;
   return ntouched;
@@ -351,6 +353,10 @@ int oracle_tsdf_integrate(oracle_tsdf *o, const uint16_t *depth, const double *T
 }
 
 long long oracle_tsdf_last_updated_voxels(const oracle_tsdf *o) { return o->last_updated_voxels; }
+int oracle_tsdf_last_touched(const oracle_tsdf *o, int *keys) {
+  if (keys) for (int i = 0; i < o->last_touched_blocks; i++) keys[i] = o->last_touched_keys[i];
+  return o->last_touched_blocks;
+}
 int oracle_tsdf_num_blocks(const oracle_tsdf *o) { return o->nblocks; }
 void oracle_tsdf_block_keys(const oracle_tsdf *o, int *keys) { for (int i = 0; i < o->nblocks; i++) keys[i] = o->blocks[i].key; }
 int oracle_tsdf_read_block(const oracle_tsdf *o, int key, float *sdf, float *weight) {
