@@ -27,6 +27,16 @@ extern "C" {
 
 void emul_set_rcp_bias(int ulps) { er_voxel_rcp_bias = ulps; }
 
+static int g_pixel_form = 1;
+void emul_set_pixel_form(int form) { g_pixel_form = form; }     // 1 = voxel_pixel, 2 = voxel_pixel_v2
+
+// the two forms on one projected voxel (for randomised edge-case sweeps)
+int emul_pixel(int form, float fx, float fy, float cx, float cy, int cols, int rows, float t0, float t1, float t2) {
+  VoxelConsts v{};
+  v.fx = fx; v.fy = fy; v.cx = cx; v.cy = cy; v.cols = cols; v.rows = rows;
+  return form == 2 ? voxel_pixel_v2(v, t0, t1, t2) : voxel_pixel(v, t0, t1, t2);
+}
+
 void emul_thresholds(double trunc, float* out3) { er_voxel_thresholds(trunc, &out3[0], &out3[1], &out3[2]); }
 
 // One IntegrateVolumeUnit call: frame (scaled depth, T camera->world, Tinv = its inverse, both row-major double[16])
@@ -57,9 +67,10 @@ long long emul_integrate_block(const float* scaled, int cols, int rows, float fx
         const float s2 = __fadd_rn(__fmul_rn(tinv[8], gx), __fmul_rn(tinv[9], gy));
         const float rx = __fsub_rn(gx, tx), ry = __fsub_rn(gy, ty), rz = __fsub_rn(gz, tz);
         const float rxy2 = __fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry));
-        const int p = voxel_pixel(v, __fadd_rn(__fadd_rn(s0, __fmul_rn(tinv[2], gz)), tinv[3]),
-                                  __fadd_rn(__fadd_rn(s1, __fmul_rn(tinv[6], gz)), tinv[7]),
-                                  __fadd_rn(__fadd_rn(s2, __fmul_rn(tinv[10], gz)), tinv[11]));
+        const float t0 = __fadd_rn(__fadd_rn(s0, __fmul_rn(tinv[2], gz)), tinv[3]);
+        const float t1 = __fadd_rn(__fadd_rn(s1, __fmul_rn(tinv[6], gz)), tinv[7]);
+        const float t2 = __fadd_rn(__fadd_rn(s2, __fmul_rn(tinv[10], gz)), tinv[11]);
+        const int p = g_pixel_form == 2 ? voxel_pixel_v2(v, t0, t1, t2) : voxel_pixel(v, t0, t1, t2);
         const float dp = (p >= 0) ? scaled[p] : 0.0f;
         const float sq = __fadd_rn(rxy2, __fmul_rn(rz, rz));
         const size_t l = ((size_t)i * kRes + j) * kRes + k;

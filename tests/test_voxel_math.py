@@ -35,6 +35,9 @@ def emul():
                                        dp, dp, C.c_int, fp, fp]
     L.emul_set_rcp_bias.argtypes = [C.c_int]
     L.emul_thresholds.argtypes = [C.c_double, fp]
+    L.emul_set_pixel_form.argtypes = [C.c_int]
+    L.emul_pixel.restype = C.c_int
+    L.emul_pixel.argtypes = [C.c_int] + [C.c_float] * 4 + [C.c_int, C.c_int] + [C.c_float] * 3
     return L
 
 
@@ -108,3 +111,67 @@ def test_threshold_helper_reproduces_the_double_comparisons(emul):
         assert float(lo) >= -trunc and float(np.nextafter(lo, np.float32(-np.inf))) < -trunc
         assert float(hi) >= trunc and float(np.nextafter(hi, np.float32(-np.inf))) < trunc
         assert abs(float(eps) - (trunc + 1e-4)) < 1e-7
+
+
+# ------------------------------------------------------------------------------------------------ second pixel form
+def ref_pixel(fx, fy, cx, cy, cols, rows, t0, t1, t2):
+    """TSDFVolume.cpp:77-81 in numpy float32/float64 (the oracle's expression, one voxel)."""
+    f = np.float32
+    with np.errstate(all="ignore"):
+        if not (f(t2) > 0):
+            return -1
+        px = f(f(f(t0) * f(fx)) / f(t2)) + f(cx)
+        py = f(f(f(t1) * f(fy)) / f(t2)) + f(cy)
+        rx, ry = np.floor(np.float64(px) + 0.5), np.floor(np.float64(py) + 0.5)
+    if not (np.isfinite(rx) and np.isfinite(ry)):
+        return -1                                   # (int) of NaN / inf is INT_MIN on x86: fails the bound test
+    if 0 <= rx < cols and 0 <= ry < rows:
+        return int(ry) * cols + int(rx)
+    return -1
+
+
+def test_both_pixel_forms_equal_the_reference_on_edge_cases(emul):
+    """Pixel coordinates a few ulps either side of every rounding boundary (k + 0.5), of the image border (-0.5,
+    dim - 0.5), depths inside and outside the fast-division range, huge / infinite / NaN operands."""
+    rng = np.random.default_rng(20260922)
+    cam = (525.0, 525.0, 319.5, 239.5, 640, 480)
+    f32 = np.float32
+    cases = []
+    for _ in range(20000):
+        t2 = f32(10.0 ** rng.uniform(-4.5, 6.5))
+        kx = rng.integers(-2, 643)
+        ky = rng.integers(-2, 483)
+        # aim at the boundary kx - 0.5 (between pixels kx - 1 and kx), then step a few ulps around it
+        t0 = f32((kx - 0.5 - cam[2]) * float(t2) / cam[0])
+        t1 = f32((ky - 0.5 - cam[3]) * float(t2) / cam[1])
+        for _ in range(int(rng.integers(0, 6))):
+            t0 = np.nextafter(t0, f32(rng.choice([-np.inf, np.inf])))
+        for _ in range(int(rng.integers(0, 6))):
+            t1 = np.nextafter(t1, f32(rng.choice([-np.inf, np.inf])))
+        cases.append((t0, t1, t2))
+    special = [0.0, -0.0, 1e-3, 9.99e-4, 1e6, 1.0001e6, 1e-30, 1e30, 3e38, -1.0, np.inf, -np.inf, np.nan, 1.0, 2.5]
+    for a in special:
+        for b in special:
+            for c in special:
+                cases.append((f32(a), f32(b), f32(c)))
+    bad = 0
+    for (t0, t1, t2) in cases:
+        want = ref_pixel(*cam, t0, t1, t2)
+        for form in (1, 2):
+            got = emul.emul_pixel(form, *[C.c_float(x) for x in cam[:4]], cam[4], cam[5], C.c_float(t0), C.c_float(t1), C.c_float(t2))
+            if got != want:
+                bad += 1
+                assert bad < 5, (form, float(t0), float(t1), float(t2), got, want)
+    assert bad == 0
+
+
+@pytest.mark.parametrize("bias", [0, -2, 2])
+def test_second_pixel_form_matches_oracle_on_scenes(oracle, emul, bias):
+    emul.emul_set_rcp_bias(bias)
+    emul.emul_set_pixel_form(2)
+    try:
+        run_scene(oracle, emul, helpers.scene_room(n=3))
+        run_scene(oracle, emul, helpers.scene_camera(n=2))
+    finally:
+        emul.emul_set_rcp_bias(0)
+        emul.emul_set_pixel_form(1)
