@@ -8,6 +8,7 @@
 // order, and the squared camera distance.  tests/test_voxel_math.py compares the result, bit for bit, with the
 // oracle's IntegrateVolumeUnit on the same block, frame and scaled depth.
 #include <cstddef>
+#include <vector>
 
 #include "er_voxel_math.h"
 
@@ -26,6 +27,9 @@ struct VoxelConsts {
 extern "C" {
 
 void emul_set_rcp_bias(int ulps) { er_voxel_rcp_bias = ulps; }
+
+static int g_tight = 0;
+void emul_set_tight_classification(int on) { g_tight = on; }
 
 static int g_pixel_form = 1;
 void emul_set_pixel_form(int form) { g_pixel_form = form; }     // 1 = voxel_pixel, 2 = voxel_pixel_v2
@@ -77,6 +81,104 @@ long long emul_integrate_block(const float* scaled, int cols, int rows, float fx
         if (voxel_finish(v, dp, sq, sdf[l], weight[l])) updated++;
       }
   return updated;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Property check of the conservative classification (classify_ball, er_voxel_math.h) on one block and one frame:
+// every 4^3 sub-brick is classified the way classify_kernel does it (8^3 brick ball first, then the eight sub-brick
+// balls) and then evaluated voxel by voxel with the exact path on fresh voxels.
+//   SKIP must mean: no voxel is updated;   ONE must mean: every voxel is updated with tsdf == 1.
+// The depth pyramids are rebuilt here from `scaled` with the semantics of touch_kernel: (min, max) over aligned
+// 16 / 8 / 4 pixel tiles, pixels outside the image counting as 0.
+// out[0..2] = sub-bricks classified SKIP / ONE / FULL, out[3] = violations, out[4] = FULL sub-bricks in which no
+// voxel was updated, out[5] = FULL sub-bricks in which every voxel got tsdf == 1 (the slack of the classification).
+// ---------------------------------------------------------------------------------------------------------------
+struct ClassifyConsts : VoxelConsts {
+  int ntx;
+  const er_tile_t *tiles, *tiles8, *tiles4;
+};
+
+static void build_level(const float* scaled, int cols, int rows, int ntx, int nty, int edge, std::vector<er_tile_t>& out) {
+  const int per = kErTile / edge, w = ntx * per, h = nty * per;
+  out.assign((size_t)w * h * kErMaxFusion, er_tile_t{0.0f, 0.0f});
+  for (int ty = 0; ty < h; ty++)
+    for (int tx = 0; tx < w; tx++) {
+      float mn = 1e30f, mx = 0.0f;
+      for (int y = ty * edge; y < (ty + 1) * edge; y++)
+        for (int x = tx * edge; x < (tx + 1) * edge; x++) {
+          const float s = (x < cols && y < rows) ? scaled[(size_t)y * cols + x] : 0.0f;
+          mn = fminf(mn, s);
+          mx = fmaxf(mx, s);
+        }
+      out[((size_t)ty * w + tx) * kErMaxFusion] = er_tile_t{mn, mx};             // frame slot 0
+    }
+}
+
+void emul_check_classification(const float* scaled, int cols, int rows, float fx, float fy, float cx, float cy, double ul_d,
+                               double trunc, const double* T, const double* Tinv, int key, long long* out) {
+  ClassifyConsts v;
+  v.fx = fx; v.fy = fy; v.cx = cx; v.cy = cy; v.cols = cols; v.rows = rows; v.trunc_d = trunc;
+  er_voxel_thresholds(trunc, &v.thr_neg, &v.thr_one, &v.trunc_eps);
+  v.ntx = (cols + kErTile - 1) / kErTile;
+  const int nty = (rows + kErTile - 1) / kErTile;
+  std::vector<er_tile_t> l16, l8, l4;
+  build_level(scaled, cols, rows, v.ntx, nty, 16, l16);
+  build_level(scaled, cols, rows, v.ntx, nty, 8, l8);
+  build_level(scaled, cols, rows, v.ntx, nty, 4, l4);
+  v.tiles = l16.data(); v.tiles8 = l8.data(); v.tiles4 = l4.data();
+  float P[15];                                                    // s_pose row of classify_kernel
+  for (int i = 0; i < 12; i++) P[i] = (float)Tinv[i];
+  P[12] = (float)T[3]; P[13] = (float)T[7]; P[14] = (float)T[11];
+  const float ul = (float)ul_d;
+  const float R8 = (float)(1.7320508 * 3.5 * ul_d) + 1e-4f;
+  const float R4 = (float)(1.7320508 * 1.5 * ul_d) + 1e-4f;
+  const int xi = key / (kGridDim * kGridDim), yi = (key / kGridDim) % kGridDim, zi = key % kGridDim;
+  const float xs = (float)((double)((xi - kGridHalf) * kRes) * ul_d);
+  const float ys = (float)((double)((yi - kGridHalf) * kRes) * ul_d);
+  const float zs = (float)((double)((zi - kGridHalf) * kRes) * ul_d);
+  long long n_cls[3] = {0, 0, 0}, bad = 0, full_idle = 0, full_one = 0;
+#pragma omp parallel for reduction(+ : bad, full_idle, full_one) reduction(+ : n_cls[:3])
+  for (int brick = 0; brick < 512; brick++) {
+    const float bx = (float)((xi - kGridHalf) * kRes + (brick >> 6) * 8);
+    const float by = (float)((yi - kGridHalf) * kRes + ((brick >> 3) & 7) * 8);
+    const float bz = (float)((zi - kGridHalf) * kRes + (brick & 7) * 8);
+    int cls[8];
+    const int c8 = g_tight ? classify_ball<true>(v, P, 0, (bx + 3.5f) * ul, (by + 3.5f) * ul, (bz + 3.5f) * ul, R8, 3.5f * ul)
+                           : classify_ball(v, P, 0, (bx + 3.5f) * ul, (by + 3.5f) * ul, (bz + 3.5f) * ul, R8);
+    for (int q = 0; q < 8; q++) {
+      const float qx = (bx + 1.5f + 4.0f * ((q >> 2) & 1)) * ul, qy = (by + 1.5f + 4.0f * ((q >> 1) & 1)) * ul,
+                  qz = (bz + 1.5f + 4.0f * (q & 1)) * ul;
+      cls[q] = (c8 != 2) ? c8 : (g_tight ? classify_ball<true>(v, P, 0, qx, qy, qz, R4, 1.5f * ul) : classify_ball(v, P, 0, qx, qy, qz, R4));
+    }
+    for (int q = 0; q < 8; q++) {
+      int n_upd = 0, n_one = 0;
+      for (int l = 0; l < 64; l++) {
+        const int i = (brick >> 6) * 8 + ((q >> 2) & 1) * 4 + (l >> 4);
+        const int j = ((brick >> 3) & 7) * 8 + ((q >> 1) & 1) * 4 + ((l >> 2) & 3);
+        const int k = (brick & 7) * 8 + (q & 1) * 4 + (l & 3);
+        const float gx = (float)((double)i * ul_d + (double)xs);
+        const float gy = (float)((double)j * ul_d + (double)ys);
+        const float gz = (float)((double)k * ul_d + (double)zs);
+        const float t0 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[0], gx), __fmul_rn(P[1], gy)), __fmul_rn(P[2], gz)), P[3]);
+        const float t1 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[4], gx), __fmul_rn(P[5], gy)), __fmul_rn(P[6], gz)), P[7]);
+        const float t2 = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(P[8], gx), __fmul_rn(P[9], gy)), __fmul_rn(P[10], gz)), P[11]);
+        const int p = voxel_pixel(v, t0, t1, t2);
+        const float dp = (p >= 0) ? scaled[p] : 0.0f;
+        const float rx = __fsub_rn(gx, P[12]), ry = __fsub_rn(gy, P[13]), rz = __fsub_rn(gz, P[14]);
+        const float sq = __fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz));
+        float sdf = 0.0f, w = 0.0f;
+        const int u = voxel_finish(v, dp, sq, sdf, w);
+        n_upd += (u != 0);
+        n_one += (u == 2);
+      }
+      n_cls[cls[q]]++;
+      if (cls[q] == 0 && n_upd != 0) bad++;
+      if (cls[q] == 1 && n_one != 64) bad++;
+      if (cls[q] == 2 && n_upd == 0) full_idle++;
+      if (cls[q] == 2 && n_one == 64) full_one++;
+    }
+  }
+  out[0] = n_cls[0]; out[1] = n_cls[1]; out[2] = n_cls[2]; out[3] = bad; out[4] = full_idle; out[5] = full_one;
 }
 
 }  // extern "C"

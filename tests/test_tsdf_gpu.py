@@ -214,29 +214,7 @@ def test_roundtrip_properties_full_size():
     assert np.allclose(s1, s2, atol=2e-7)       # (s*1 + s)/2 == s up to one rounding
 
 
-def _random_scene(seed, n, cols=640, rows=480, holes=True):
-    """Random camera poses inside the room (any orientation, sometimes hugging a wall), analytic room depth with
-    random invalid holes, far spikes beyond integration_trunc and near spikes: stresses the conservative
-    SKIP / ONE / FULL classification (camera-plane straddling bricks, image borders, depth discontinuities)."""
-    rng = np.random.default_rng(seed)
-    poses, frames = [], []
-    for _ in range(n):
-        c = rng.uniform(0.45, 2.55, size=3)
-        R = synth.rot_axis(rng.normal(size=3), rng.uniform(0, np.pi))
-        poses.append(synth.make_pose(R, c))
-    poses = synth.quantize_log(np.array(poses))
-    fx = 525.0 * cols / 640.0
-    d = synth.room_depth(poses, w=cols, h=rows, fx=fx, fy=fx, cx=(cols - 1) / 2.0, cy=(rows - 1) / 2.0, bumps=True)
-    if holes:
-        for f in range(n):
-            m = rng.random((rows, cols))
-            d[f][m < 0.02] = 0                                   # dropouts
-            y0, x0 = rng.integers(0, rows - 40), rng.integers(0, cols - 60)
-            d[f][y0:y0 + 40, x0:x0 + 60] = 0                     # a rectangular hole
-            y1, x1 = rng.integers(0, rows - 30), rng.integers(0, cols - 30)
-            d[f][y1:y1 + 30, x1:x1 + 30] = rng.integers(300, 500)  # a near object (depth discontinuity)
-            d[f][m > 0.9995] = 6000                              # beyond integration_trunc -> scaled depth 0
-    return d, poses, (fx, fx, (cols - 1) / 2.0, (rows - 1) / 2.0)
+_random_scene = helpers.random_scene          # shared with the CPU classification property test
 
 
 @pytest.mark.parametrize("seed", [1, 2, 3])
