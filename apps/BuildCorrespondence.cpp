@@ -6,7 +6,8 @@
 //
 // Differences from the reference, all outside the numerics: the accepted pairs of --registration are aligned in
 // one batched call (many pairs in flight on the GPU) instead of one OpenMP thread per pair; extra flags
-// --device N, --fixed_iters (run exactly 20 ICP iterations), --bench_json FILE.
+// --device N, --devices A,B,.. (ICP pairs sharded over several GPUs in-process), --fixed_iters (run exactly 20 ICP
+// iterations), --bench_json FILE.
 #include <chrono>
 #include <cstdio>
 #include <iostream>
@@ -38,6 +39,7 @@ static int print_help() {
   std::cout << "    --redux <log_file>              : use transformations in <log_file> as constraints" << std::endl;
   std::cout << "B200 build only:" << std::endl;
   std::cout << "    --device <n> --fixed_iters --bench_json <file>" << std::endl;
+  std::cout << "    --devices <a,b,...>             : ICP on several GPUs (fragments replicated, accepted pairs dealt round-robin)" << std::endl;
   return 0;
 }
 
@@ -58,14 +60,19 @@ struct CorresApp {
   int num = 0, interval = 50;
   double length = 3.0;
   int device = 0;
+  std::vector<int> extra_devices;    // --devices a,b,c: further GPUs; accepted pairs are dealt round-robin over all of them
   bool fixed_iters = false;
 
   std::vector<PointCloudXYZN> pointclouds;
-  std::vector<er_cloud*> clouds;
+  std::vector<er_cloud*> clouds;                       // on `device`: gate, ICP share, correspondences
+  std::vector<std::vector<er_cloud*>> replica;         // replica[k][i]: fragment i on extra_devices[k] (ICP share only)
   long icp_pairs = 0, icp_iterations = 0;
   double icp_ms = 0;
 
-  ~CorresApp() { for (auto* c : clouds) er_cloud_free(c); }
+  ~CorresApp() {
+    for (auto* c : clouds) er_cloud_free(c);
+    for (auto& r : replica) for (auto* c : r) er_cloud_free(c);
+  }
 
   int redux_index(int i, int j) const { return i + j * num; }        // GetReduxIndex, CorresApp.h:58-60
 
@@ -170,6 +177,18 @@ struct CorresApp {
         { std::cerr << "er_cloud_upload: " << er_last_error() << std::endl; ok = false; }
       }
     }
+    // fragments are replicated on every further device (4.8 MB each; the pair list is what is sharded)
+    replica.assign(extra_devices.size(), std::vector<er_cloud*>((size_t)num, nullptr));
+    for (size_t k = 0; k < extra_devices.size() && ok; k++) {
+#pragma omp parallel for num_threads(8) schedule(dynamic)
+      for (int i = 0; i < num; i++) {
+        replica[k][i] = er_cloud_upload(extra_devices[k], pointclouds[i].xyz.data(), pointclouds[i].nrm.data(), pointclouds[i].size(), cell);
+        if (!replica[k][i]) {
+#pragma omp critical
+          { std::cerr << "er_cloud_upload (device " << extra_devices[k] << "): " << er_last_error() << std::endl; ok = false; }
+        }
+      }
+    }
     return ok;
   }
 
@@ -256,11 +275,39 @@ struct CorresApp {
       std::memcpy(&Tin[16 * (size_t)p], d.T, sizeof d.T);
     }
     const auto t0 = std::chrono::steady_clock::now();
-    if (er_icp_align_batch(clouds.data(), num, ti.data(), si.data(), np, Tin.data(), reg_dist, 20, 1e-6, fixed_iters ? 1 : 0,
-                           Tout.data(), iters.data(), fit.data())) {
-      std::cerr << "er_icp_align_batch: " << er_last_error() << std::endl;
-      return false;
+    // pairs are independent (CorresApp.cpp:220 runs them from an OpenMP loop): share k of the list goes to device k,
+    // one host thread per device, results land in the slots of the original list -- no exchange between devices
+    const int ndev = 1 + (int)extra_devices.size();
+    std::vector<std::string> errs((size_t)ndev);
+#pragma omp parallel for num_threads(ndev) schedule(static, 1)
+    for (int k = 0; k < ndev; k++) {
+      std::vector<int> sel;
+      for (int p = k; p < np; p += ndev) sel.push_back(p);
+      const int m = (int)sel.size();
+      if (m == 0) continue;
+      std::vector<int> t2(m), s2(m), it2(m);
+      std::vector<double> Ti2(16 * (size_t)m), To2(16 * (size_t)m), f2(m);
+      for (int q = 0; q < m; q++) {
+        t2[q] = ti[sel[q]]; s2[q] = si[sel[q]];
+        std::memcpy(&Ti2[16 * (size_t)q], &Tin[16 * (size_t)sel[q]], 16 * sizeof(double));
+      }
+      er_cloud* const* cl = (k == 0) ? clouds.data() : replica[(size_t)k - 1].data();
+      if (er_icp_align_batch(cl, num, t2.data(), s2.data(), m, Ti2.data(), reg_dist, 20, 1e-6, fixed_iters ? 1 : 0, To2.data(),
+                             it2.data(), f2.data())) {
+        errs[(size_t)k] = er_last_error();          // the error text is per host thread
+        continue;
+      }
+      for (int q = 0; q < m; q++) {
+        std::memcpy(&Tout[16 * (size_t)sel[q]], &To2[16 * (size_t)q], 16 * sizeof(double));
+        iters[sel[q]] = it2[q];
+        fit[sel[q]] = f2[q];
+      }
     }
+    for (int k = 0; k < ndev; k++)
+      if (!errs[(size_t)k].empty()) {
+        std::cerr << "er_icp_align_batch (device " << (k == 0 ? device : extra_devices[(size_t)k - 1]) << "): " << errs[(size_t)k] << std::endl;
+        return false;
+      }
     icp_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     for (int p = 0; p < np; p++) {
       FramedTransformation& d = corres_traj.data[todo[p]];
@@ -342,6 +389,20 @@ int main(int argc, char* argv[]) {
   double reg_dist = 0, reg_ratio = 0;
   int reg_num = 0, num = 0;
   parse_argument(argc, argv, "--device", app.device);
+  std::string devices;
+  if (parse_argument(argc, argv, "--devices", devices) > 0) {          // "0,1,2": the first is the main device
+    std::vector<int> all;
+    for (size_t pos = 0; pos < devices.size();) {
+      size_t end = devices.find(',', pos);
+      if (end == std::string::npos) end = devices.size();
+      if (end > pos) all.push_back(std::atoi(devices.substr(pos, end - pos).c_str()));
+      pos = end + 1;
+    }
+    if (!all.empty()) {
+      app.device = all[0];
+      app.extra_devices.assign(all.begin() + 1, all.end());
+    }
+  }
   parse_argument(argc, argv, "--bench_json", bench_json);
   app.fixed_iters = find_switch(argc, argv, "--fixed_iters");
 

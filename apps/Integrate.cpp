@@ -6,7 +6,10 @@
 // numeric work (ScaleDepth, Integrate, Reproject, SaveWorld) is the library's.  Differences, all at the edges:
 //   * "-oni <file>" names the raw depth container of apps/er_io.h (OpenNI is not available); "-dev" cannot open;
 //   * frames are pulled synchronously, so there is no 10 x 300 ms end-of-stream timeout;
-//   * extra flags: --device N, --max_blocks N, --fusion N (frames per fused launch), --bench_json FILE, and
+//   * extra flags: --device N, --devices A,B,.. (one volume partitioned by blocks over several GPUs: device k owns
+//     the blocks with (xi+yi+zi) % n == k, every device sees every frame, the extracted voxels are concatenated --
+//     no halo is needed, a voxel update reads only depth + pose), --max_blocks N, --fusion N (frames per fused
+//     launch), --bench_json FILE, and
 //     --voxel_size M / --tsdf_trunc M / --block_res 64: the reference's constructor constants
 //     (TSDFVolume.cpp:10-11,57), defaulting to the reference values 3/512, 0.03, 64.
 #include <chrono>
@@ -39,6 +42,7 @@ static int print_help() {
   std::cout << "    -dev <device> (default), -oni <oni_file>" << std::endl;
   std::cout << "B200 build only:" << std::endl;
   std::cout << "    --device <n> --max_blocks <n> --fusion <1..32> --bench_json <file>" << std::endl;
+  std::cout << "    --devices <a,b,...>             : partition the volume's blocks over several GPUs" << std::endl;
   std::cout << "    --voxel_size <m> (3/512) --tsdf_trunc <m> (0.03) --block_res <n> (64, fixed)" << std::endl;
   return 0;
 }
@@ -49,13 +53,14 @@ struct App {
   int ctr_num = 0, ctr_resolution = 8, ctr_interval = 50, start_from = -1, end_at = 100000000;
   double ctr_length = 3.0;
   int device = 0, max_blocks = 4096, fusion = 32, block_res = 64;
+  std::vector<int> devices;                                // empty: {device}
   double voxel_size = 0.0, tsdf_trunc = 0.0;               // 0 = the reference constants
   std::string bench_json;
 
   CameraParam camera;
   Trajectory traj, seg_traj, pose_traj;
   std::vector<float> grids;
-  er_tsdf* vol = nullptr;
+  std::vector<er_tsdf*> vols;                              // one per device; vols[k] owns the blocks of partition k
   int cols = 640, rows = 480;
   int frame_id = 0;
   bool exit_ = false;
@@ -96,11 +101,17 @@ struct App {
         std::fprintf(stderr, "Trajectory created from pose and segment trajectories.\n");
       }
     }
-    vol = er_tsdf_create(device, cols, rows, voxel_size, block_res, tsdf_trunc, (size_t)max_blocks);
-    if (!vol) return fail("er_tsdf_create");
-    if (er_tsdf_set_camera(vol, camera.fx, camera.fy, camera.cx, camera.cy, camera.integration_trunc)) return fail("set_camera");
-    if (er_tsdf_set_fusion(vol, fusion)) return fail("set_fusion");
-    if (ctr_num > 0 && er_tsdf_set_control_grids(vol, grids.data(), ctr_num, ctr_resolution, (float)ctr_length)) return fail("set_control_grids");
+    if (devices.empty()) devices.push_back(device);
+    const int ndev = (int)devices.size();
+    for (int k = 0; k < ndev; k++) {
+      er_tsdf* vol = er_tsdf_create(devices[k], cols, rows, voxel_size, block_res, tsdf_trunc, (size_t)max_blocks);
+      if (!vol) return fail("er_tsdf_create");
+      vols.push_back(vol);
+      if (er_tsdf_set_camera(vol, camera.fx, camera.fy, camera.cx, camera.cy, camera.integration_trunc)) return fail("set_camera");
+      if (er_tsdf_set_fusion(vol, fusion)) return fail("set_fusion");
+      if (ctr_num > 0 && er_tsdf_set_control_grids(vol, grids.data(), ctr_num, ctr_resolution, (float)ctr_length)) return fail("set_control_grids");
+      if (ndev > 1 && er_tsdf_set_partition(vol, k, ndev)) return fail("set_partition");
+    }
     return true;
   }
 
@@ -143,25 +154,42 @@ struct App {
         processed++;
       }
       if (nb > 0) {
-        if (ctr_num > 0) {
-          if (er_tsdf_integrate_ctr_batch(vol, batch.data(), poses.data(), traj.data[0].T, seg_traj.data[0].T, segs.data(),
-                                          chunks.data(), nb))
-            return fail("er_tsdf_integrate_ctr_batch");
-        } else if (er_tsdf_integrate_batch(vol, batch.data(), poses.data(), nb)) {
-          return fail("er_tsdf_integrate_batch");
+        // every device integrates the same frames into its own share of the blocks (one host thread per device)
+        const int ndev = (int)vols.size();
+        std::vector<std::string> errs((size_t)ndev);
+#pragma omp parallel for num_threads(ndev) schedule(static, 1)
+        for (int k = 0; k < ndev; k++) {
+          int rc;
+          if (ctr_num > 0)
+            rc = er_tsdf_integrate_ctr_batch(vols[k], batch.data(), poses.data(), traj.data[0].T, seg_traj.data[0].T, segs.data(),
+                                             chunks.data(), nb);
+          else
+            rc = er_tsdf_integrate_batch(vols[k], batch.data(), poses.data(), nb);
+          if (rc) errs[(size_t)k] = er_last_error();       // the error text is per host thread
         }
+        for (int k = 0; k < ndev; k++)
+          if (!errs[(size_t)k].empty()) {
+            std::cerr << (ctr_num > 0 ? "er_tsdf_integrate_ctr_batch: " : "er_tsdf_integrate_batch: ") << errs[(size_t)k] << std::endl;
+            return false;
+          }
       }
     }
-    return er_tsdf_sync(vol) == 0 || fail("er_tsdf_sync");
+    for (er_tsdf* vol : vols)
+      if (er_tsdf_sync(vol)) return fail("er_tsdf_sync");
+    return true;
   }
 
   // TSDFVolume::SaveWorld (TSDFVolume.cpp:104-132)
   bool save_world() {
+    std::vector<float> pts;
     size_t n = 0;
-    if (er_tsdf_extract(vol, nullptr, 0, &n)) return fail("er_tsdf_extract");
-    std::vector<float> pts(4 * (n ? n : 1));
-    size_t m = 0;
-    if (n && er_tsdf_extract(vol, pts.data(), n, &m)) return fail("er_tsdf_extract");
+    for (er_tsdf* vol : vols) {                            // the partitions are disjoint: concatenate
+      size_t nk = 0, mk = 0;
+      if (er_tsdf_extract(vol, nullptr, 0, &nk)) return fail("er_tsdf_extract");
+      pts.resize(4 * (n + nk) + 4);
+      if (nk && er_tsdf_extract(vol, pts.data() + 4 * n, nk, &mk)) return fail("er_tsdf_extract");
+      n += nk;
+    }
     if (!save_pcd_xyzi(pcd_filename, pts.data(), n)) { std::cerr << "cannot write " << pcd_filename << std::endl; return false; }
     std::printf("%d voxel points have been written.\n", (int)n);
     return true;
@@ -196,6 +224,15 @@ int main(int argc, char* argv[]) {
   parse_argument(argc, argv, "--length", app.ctr_length);
   parse_argument(argc, argv, "--interval", app.ctr_interval);
   parse_argument(argc, argv, "--device", app.device);
+  std::string devices;
+  if (parse_argument(argc, argv, "--devices", devices) > 0) {
+    for (size_t pos = 0; pos < devices.size();) {
+      size_t end = devices.find(',', pos);
+      if (end == std::string::npos) end = devices.size();
+      if (end > pos) app.devices.push_back(std::atoi(devices.substr(pos, end - pos).c_str()));
+      pos = end + 1;
+    }
+  }
   parse_argument(argc, argv, "--max_blocks", app.max_blocks);
   parse_argument(argc, argv, "--fusion", app.fusion);
   parse_argument(argc, argv, "--bench_json", app.bench_json);
@@ -221,6 +258,6 @@ int main(int argc, char* argv[]) {
       std::fclose(f);
     }
   }
-  if (app.vol) er_tsdf_destroy(app.vol);
+  for (er_tsdf* vol : app.vols) er_tsdf_destroy(vol);
   return 0;        // like the reference, failures are reported on the console, not through the exit code
 }
