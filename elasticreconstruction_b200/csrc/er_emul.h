@@ -59,6 +59,11 @@ static inline float er_emul_fadd_rz(float a, float b) {   // add.rz.f32 through 
 }
 #define __float2int_rd(a) er_emul_f2i_rd(a)
 #define __fadd_rz(a, b) er_emul_fadd_rz((a), (b))
+#define __dadd_rn(a, b) ((double)(a) + (double)(b))
+#define __dmul_rn(a, b) ((double)(a) * (double)(b))
+static inline int __double2int_rd(double x) {        // cvt.rmi.s32.f64 (callers range-check first)
+  return (int)floor(x);
+}
 static inline int __float_as_int(float f) { int i; std::memcpy(&i, &f, 4); return i; }
 static inline unsigned __float_as_uint(float f) { unsigned i; std::memcpy(&i, &f, 4); return i; }
 static inline float __int_as_float(int i) { float f; std::memcpy(&f, &i, 4); return f; }

@@ -181,4 +181,93 @@ void emul_check_classification(const float* scaled, int cols, int rows, float fx
   out[0] = n_cls[0]; out[1] = n_cls[1]; out[2] = n_cls[2]; out[3] = bad; out[4] = full_idle; out[5] = full_one;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Property check of the touch kernel's block keys on one frame (estimate_block / touch_pixel_index, er_voxel_math.h,
+// and the tile shortcut of touch_kernel restated from er_tsdf.cu): against the reference's double sequence
+// (UVD2XYZ TSDFVolume.h:40-49, TSDFVolume.cpp:49-53),
+//   * every valid pixel's block from touch_pixel_index must be the reference's block;
+//   * whenever the 8 frustum corners of a 16x16 tile (corner pixels x {min, max} raw depth) agree on one block
+//     without raising `risky`, every valid pixel of the tile must lie in that block.
+// out[0] = valid pixels, out[1] = pixels that took the exact fallback, out[2] = tiles with a valid pixel,
+// out[3] = tiles the shortcut declared uniform, out[4] = violations.
+// ---------------------------------------------------------------------------------------------------------------
+struct TouchConsts {
+  float fx, fy, cx, cy;
+  double ul, inv_ul, inv_fx, inv_fy;
+};
+
+static void reference_block(const TouchConsts& v, const double* T, int u, int vr, unsigned d, int blk[3]) {
+  const double z = d / 1000.0;
+  const double x = ((float)u - v.cx) * z / v.fx;
+  const double y = ((float)vr - v.cy) * z / v.fy;
+  for (int r = 0; r < 3; r++) {
+    const double w = ((T[r * 4 + 0] * x + T[r * 4 + 1] * y) + T[r * 4 + 2] * z) + T[r * 4 + 3];
+    blk[r] = ((int)floor(w / v.ul + 0.5) + kGridHalf * kRes) / kRes;
+  }
+}
+
+void emul_check_touch(const unsigned short* depth, int cols, int rows, float fx, float fy, float cx, float cy, double ul,
+                      const double* T, long long* out) {
+  TouchConsts v;
+  v.fx = fx; v.fy = fy; v.cx = cx; v.cy = cy; v.ul = ul;
+  v.inv_ul = 1.0 / ul; v.inv_fx = 1.0 / (double)fx; v.inv_fy = 1.0 / (double)fy;      // er_tsdf_set_camera / create
+  float Tf[12];
+  for (int i = 0; i < 12; i++) Tf[i] = (float)T[i];
+  long long n_valid = 0, n_exact = 0, n_tiles = 0, n_uniform = 0, bad = 0;
+  const int ntx = (cols + kErTile - 1) / kErTile, nty = (rows + kErTile - 1) / kErTile;
+#pragma omp parallel for reduction(+ : n_valid, n_exact, n_tiles, n_uniform, bad)
+  for (int t = 0; t < ntx * nty; t++) {
+    const int tx0 = (t % ntx) * kErTile, ty0 = (t / ntx) * kErTile;
+    unsigned lo = 0xFFFFFFFFu, hi = 0u;
+    for (int y = ty0; y < ty0 + kErTile && y < rows; y++)
+      for (int x = tx0; x < tx0 + kErTile && x < cols; x++) {
+        const unsigned d = depth[(size_t)y * cols + x];
+        if (d) { lo = d < lo ? d : lo; hi = d > hi ? d : hi; }
+      }
+    if (hi == 0) continue;
+    n_tiles++;
+    // tile shortcut: lanes 0..7 of warp 0 in touch_kernel
+    int first[3] = {0, 0, 0};
+    bool uniform = true;
+    for (int c = 0; c < 8; c++) {
+      const int cu = (c & 1) ? min(tx0 + kErTile - 1, cols - 1) : tx0;
+      const int cv = (c & 2) ? min(ty0 + kErTile - 1, rows - 1) : ty0;
+      const float cd = (c & 4) ? (float)hi : (float)lo;
+      int bi[3];
+      bool risky = false;
+      estimate_block(v, Tf, __fsub_rn((float)cu, v.cx), __fsub_rn((float)cv, v.cy), cd, bi, risky);
+      if (c == 0) { first[0] = bi[0]; first[1] = bi[1]; first[2] = bi[2]; }
+      const bool same = (bi[0] == first[0]) & (bi[1] == first[1]) & (bi[2] == first[2]);
+      const bool okc = same && !risky && bi[0] >= 0 && bi[0] < kGridDim && bi[1] >= 0 && bi[1] < kGridDim && bi[2] >= 0 && bi[2] < kGridDim;
+      uniform = uniform && okc;
+    }
+    if (uniform) n_uniform++;
+    for (int y = ty0; y < ty0 + kErTile && y < rows; y++)
+      for (int x = tx0; x < tx0 + kErTile && x < cols; x++) {
+        const unsigned d = depth[(size_t)y * cols + x];
+        if (!d) continue;
+        n_valid++;
+        int ref[3];
+        reference_block(v, T, x, y, d, ref);
+        const bool ref_in = ref[0] >= 0 && ref[0] < kGridDim && ref[1] >= 0 && ref[1] < kGridDim && ref[2] >= 0 && ref[2] < kGridDim;
+        // per-pixel path
+        int idx[3];
+        bool risky = false;
+        {
+          int tmp[3];
+          estimate_block(v, Tf, __fsub_rn((float)x, v.cx), __fsub_rn((float)y, v.cy), (float)d, tmp, risky);
+          if (risky) n_exact++;
+        }
+        touch_pixel_index(v, Tf, T, __fsub_rn((float)x, v.cx), __fsub_rn((float)y, v.cy), d, idx);
+        const int lim = kGridDim * kRes;
+        const bool in = idx[0] >= 0 && idx[0] < lim && idx[1] >= 0 && idx[1] < lim && idx[2] >= 0 && idx[2] < lim;
+        if (in != ref_in) bad++;
+        else if (in && (idx[0] / kRes != ref[0] || idx[1] / kRes != ref[1] || idx[2] / kRes != ref[2])) bad++;
+        if (uniform && ref_in && (ref[0] != first[0] || ref[1] != first[1] || ref[2] != first[2])) bad++;
+        if (uniform && !ref_in) bad++;
+      }
+  }
+  out[0] = n_valid; out[1] = n_exact; out[2] = n_tiles; out[3] = n_uniform; out[4] = bad;
+}
+
 }  // extern "C"

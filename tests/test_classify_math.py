@@ -76,3 +76,36 @@ def test_tighter_distance_bounds_are_still_conservative(oracle, emul):
     finally:
         emul.emul_set_tight_classification(0)
     assert tight[3] == 0 and tight[2] < base[2]
+
+
+# ------------------------------------------------------------------------------------------------ touch kernel keys
+def check_touch(emul, d, poses, cam, cols=640, rows=480, ul=3.0 / 512.0):
+    emul.emul_check_touch.argtypes = [C.POINTER(C.c_ushort), C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_double,
+                                      C.POINTER(C.c_double), C.POINTER(C.c_longlong)]
+    tot = np.zeros(5, dtype=np.int64)
+    for f in range(len(d)):
+        depth = np.ascontiguousarray(d[f], dtype=np.uint16)
+        T = np.ascontiguousarray(poses[f], dtype=np.float64)
+        out = np.zeros(5, dtype=np.int64)
+        emul.emul_check_touch(depth.ctypes.data_as(C.POINTER(C.c_ushort)), cols, rows, cam[0], cam[1], cam[2], cam[3], ul, _dp(T),
+                              out.ctypes.data_as(C.POINTER(C.c_longlong)))
+        assert out[4] == 0, "frame %d: %d block keys differ from the reference" % (f, out[4])
+        tot += out
+    return tot
+
+
+def test_touch_block_keys_match_the_reference(emul):
+    """Float estimate + exact fallback per pixel, and the tile-level frustum shortcut, against the reference's double
+    arithmetic: random views with holes and spikes, the benchmark trajectory, an odd image size, and a coarse voxel
+    size (block boundaries elsewhere)."""
+    d, poses, cam = helpers.random_scene(21, 12)
+    t1 = check_touch(emul, d, poses, cam)
+    sc = helpers.scene_room(n=6)
+    t2 = check_touch(emul, sc["frames"], sc["traj"], (525.0, 525.0, 319.5, 239.5))
+    d3, poses3, cam3 = helpers.random_scene(22, 4, 330, 247)
+    check_touch(emul, d3, poses3, cam3, 330, 247)
+    check_touch(emul, d[:4], poses[:4], cam, ul=0.012)
+    for t in (t1, t2):
+        assert t[0] > 1000000                    # valid pixels
+        assert 0 < t[1] < 0.05 * t[0]            # the exact fallback is rare but does occur
+        assert t[3] > 0.5 * t[2]                 # most tiles take the one-key shortcut
