@@ -172,7 +172,7 @@ def run_reference(args):
         "impl": "reference", "metric": "depth frames/sec into 512^3 TSDF", "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "TSDF integrate: 1000 synthetic 640x480 frames, rigid trajectory, 512^3 @ 3/512 m",
+        "config": {"workload": "TSDF integrate: 1000 synthetic 640x480 frames, rigid trajectory, 512^3 @ 3/512 m (BASELINE configs[1])",
                    "frames_per_step": fps_step, "threads": 8, "host_cores": os.cpu_count()},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
