@@ -129,8 +129,10 @@ typedef struct er_icp er_icp;
 
 /* One fragment (pcl::PointCloud<PointXYZRGBNormal> after the NaN-normal filter, CorresApp.cpp:93-98):
  * xyz and normals as n*3 floats.  Builds the uniform-grid search structure that stands in for
- * pcl::KdTreeFLANN::setInputCloud (CorresApp.cpp:148,253); cell_size must be >= every search radius
- * later used against this cloud as a target. */
+ * pcl::KdTreeFLANN::setInputCloud (CorresApp.cpp:148,253) -- bounding box on the host, counting sort by cell on the
+ * device; cell_size must be >= every search radius later used against this cloud as a target.  The caller's
+ * buffers may be reused on return.  Safe to call from several host threads at once (CorresApp.cpp:82 loads the
+ * fragments from an OpenMP loop). */
 er_cloud* er_cloud_upload(int device, const float* xyz, const float* normals, size_t n, double cell_size);
 void er_cloud_free(er_cloud* c);
 size_t er_cloud_size(const er_cloud* c);
