@@ -114,6 +114,84 @@ static void build_level(const float* scaled, int cols, int rows, int ntx, int nt
     }
 }
 
+// ---- exploration only (not product code): what would a classifier gain from exact footprint statistics?
+// mode 1: min/max of `scaled` over the exact pixel rectangle of classify_ball's footprint (no tile alignment slack)
+// mode 2: as 1, with the footprint taken from the projections of the 8 corners of the voxel-centre box (+1.5 px)
+// mode 3: as 2, plus the TIGHT distance bound
+// mode 4: footprint from the closed-form bound |u(c + o) - u(c)| <= fx * half * sum_i |a_i zc - pcx b_i| / (zc (zc - hz)),
+//         hz = half * sum_i |b_i| (a, b = rows 0 and 2 of the rotation), + 1.5 px, plus the TIGHT distance bound
+// mode 5: mode 4 on the tile pyramids (4 / 8 / 16 px levels as classify_ball) instead of exact rectangle statistics
+static int g_explore = 0;
+void emul_set_explore(int mode) { g_explore = mode; }
+
+static int classify_explore(const ClassifyConsts& v, const float* scaled, const float* P, float wx, float wy, float wz, float R,
+                            float half) {
+  const float eps = 1e-3f, trunc = (float)v.trunc_d;
+  const float pcx = P[0] * wx + P[1] * wy + P[2] * wz + P[3];
+  const float pcy = P[4] * wx + P[5] * wy + P[6] * wz + P[7];
+  const float zc = P[8] * wx + P[9] * wy + P[10] * wz + P[11];
+  if (!(zc + R > 0.0f)) return 0;
+  if (!(zc - R > 0.05f)) return 2;
+  const float dxw = wx - P[12], dyw = wy - P[13], dzw = wz - P[14];
+  const float dc = sqrtf(dxw * dxw + dyw * dyw + dzw * dzw);
+  float u0, u1, v0, v1;
+  if (g_explore >= 4) {
+    const float hz = half * (fabsf(P[8]) + fabsf(P[9]) + fabsf(P[10]));
+    const float den = 1.0f / (zc * (zc - hz));
+    const float su = fabsf(P[0] * zc - pcx * P[8]) + fabsf(P[1] * zc - pcx * P[9]) + fabsf(P[2] * zc - pcx * P[10]);
+    const float sv = fabsf(P[4] * zc - pcy * P[8]) + fabsf(P[5] * zc - pcy * P[9]) + fabsf(P[6] * zc - pcy * P[10]);
+    const float ru = v.fx * half * su * den * 1.001f + 1.5f, rv = v.fy * half * sv * den * 1.001f + 1.5f;
+    const float uc = v.fx * pcx / zc + v.cx, vc = v.fy * pcy / zc + v.cy;
+    u0 = uc - ru; u1 = uc + ru; v0 = vc - rv; v1 = vc + rv;
+  } else if (g_explore == 1) {
+    const float inv = 1.0f / (zc - R), izc = 1.0f / zc;
+    const float ru = v.fx * R * (1.0f + fabsf(pcx) * izc) * inv + 1.5f;
+    const float rv = v.fy * R * (1.0f + fabsf(pcy) * izc) * inv + 1.5f;
+    const float uc = v.fx * pcx * izc + v.cx, vc = v.fy * pcy * izc + v.cy;
+    u0 = uc - ru; u1 = uc + ru; v0 = vc - rv; v1 = vc + rv;
+  } else {
+    u0 = v0 = 1e30f; u1 = v1 = -1e30f;
+    for (int c = 0; c < 8; c++) {
+      const float ox = (c & 1) ? half : -half, oy = (c & 2) ? half : -half, oz = (c & 4) ? half : -half;
+      const float x = pcx + P[0] * ox + P[1] * oy + P[2] * oz, y = pcy + P[4] * ox + P[5] * oy + P[6] * oz;
+      const float z = zc + P[8] * ox + P[9] * oy + P[10] * oz;
+      const float u = v.fx * x / z + v.cx, w = v.fy * y / z + v.cy;
+      u0 = fminf(u0, u); u1 = fmaxf(u1, u); v0 = fminf(v0, w); v1 = fmaxf(v1, w);
+    }
+    u0 -= 1.5f; u1 += 1.5f; v0 -= 1.5f; v1 += 1.5f;
+  }
+  if (u1 < -0.5f || u0 > (float)v.cols - 0.5f || v1 < -0.5f || v0 > (float)v.rows - 0.5f) return 0;
+  const bool inside = u0 >= 0.0f && u1 <= (float)(v.cols - 1) && v0 >= 0.0f && v1 <= (float)(v.rows - 1);
+  const int px0 = max(0, (int)floorf(u0)), px1 = min(v.cols - 1, (int)ceilf(u1));
+  const int py0 = max(0, (int)floorf(v0)), py1 = min(v.rows - 1, (int)ceilf(v1));
+  float tmin = 1e30f, tmax = 0.0f;
+  if (g_explore == 5) {
+    const float wpx = fmaxf(u1 - u0, v1 - v0);
+    const int sh = wpx <= 20.0f ? 2 : (wpx <= 40.0f ? 3 : 4);
+    const int tx0 = px0 >> sh, tx1 = px1 >> sh, ty0 = py0 >> sh, ty1 = py1 >> sh;
+    if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) > 64) return 2;
+    const er_tile_t* lvl = (sh == 4 ? v.tiles : (sh == 3 ? v.tiles8 : v.tiles4));
+    const int pitch = v.ntx * (kErTile >> sh);
+    for (int ty = ty0; ty <= ty1; ty++)
+      for (int tx = tx0; tx <= tx1; tx++) {
+        const er_tile_t t = lvl[(size_t)(ty * pitch + tx) * kErMaxFusion];
+        tmin = fminf(tmin, t.x); tmax = fmaxf(tmax, t.y);
+      }
+  } else {
+    for (int y = py0; y <= py1; y++)
+      for (int x = px0; x <= px1; x++) { const float sv = scaled[(size_t)y * v.cols + x]; tmin = fminf(tmin, sv); tmax = fmaxf(tmax, sv); }
+  }
+  float near = R, far = R;
+  if (g_explore >= 3) {
+    const float h = half * (fabsf(dxw) + fabsf(dyw) + fabsf(dzw)) / dc * 1.0001f + 1e-5f;
+    near = fminf(R, h);
+    far = fminf(R, h + R * R / (2.0f * (dc - R)));
+  }
+  if (dc - near > tmax + trunc + eps) return 0;
+  if (inside && tmin > 0.002f && tmin - trunc - eps >= dc + far) return 1;
+  return 2;
+}
+
 void emul_check_classification(const float* scaled, int cols, int rows, float fx, float fy, float cx, float cy, double ul_d,
                                double trunc, const double* T, const double* Tinv, int key, long long* out) {
   ClassifyConsts v;
@@ -143,12 +221,15 @@ void emul_check_classification(const float* scaled, int cols, int rows, float fx
     const float by = (float)((yi - kGridHalf) * kRes + ((brick >> 3) & 7) * 8);
     const float bz = (float)((zi - kGridHalf) * kRes + (brick & 7) * 8);
     int cls[8];
-    const int c8 = g_tight ? classify_ball<true>(v, P, 0, (bx + 3.5f) * ul, (by + 3.5f) * ul, (bz + 3.5f) * ul, R8, 3.5f * ul)
-                           : classify_ball(v, P, 0, (bx + 3.5f) * ul, (by + 3.5f) * ul, (bz + 3.5f) * ul, R8);
+    const int c8 = g_explore ? classify_explore(v, scaled, P, (bx + 3.5f) * ul, (by + 3.5f) * ul, (bz + 3.5f) * ul, R8, 3.5f * ul)
+                   : g_tight ? classify_ball<true>(v, P, 0, (bx + 3.5f) * ul, (by + 3.5f) * ul, (bz + 3.5f) * ul, R8, 3.5f * ul)
+                             : classify_ball(v, P, 0, (bx + 3.5f) * ul, (by + 3.5f) * ul, (bz + 3.5f) * ul, R8);
     for (int q = 0; q < 8; q++) {
       const float qx = (bx + 1.5f + 4.0f * ((q >> 2) & 1)) * ul, qy = (by + 1.5f + 4.0f * ((q >> 1) & 1)) * ul,
                   qz = (bz + 1.5f + 4.0f * (q & 1)) * ul;
-      cls[q] = (c8 != 2) ? c8 : (g_tight ? classify_ball<true>(v, P, 0, qx, qy, qz, R4, 1.5f * ul) : classify_ball(v, P, 0, qx, qy, qz, R4));
+      cls[q] = (c8 != 2) ? c8
+               : g_explore ? classify_explore(v, scaled, P, qx, qy, qz, R4, 1.5f * ul)
+               : (g_tight ? classify_ball<true>(v, P, 0, qx, qy, qz, R4, 1.5f * ul) : classify_ball(v, P, 0, qx, qy, qz, R4));
     }
     for (int q = 0; q < 8; q++) {
       int n_upd = 0, n_one = 0;
