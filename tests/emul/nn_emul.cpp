@@ -76,6 +76,17 @@ void emul_nn_search(void* h, const float* q, int m, int* idx, float* d2) {
   }
 }
 
+// exploration counters (not product code): candidate points compared and cell columns examined by emul_nn_coop
+static long long g_points = 0, g_items = 0, g_runs = 0;
+void emul_nn_counters(long long* out, int reset) {
+  out[0] = g_points; out[1] = g_items; out[2] = g_runs;
+  if (reset) g_points = g_items = g_runs = 0;
+}
+// exploration: seed[i] >= 0 names a target point (original index) whose distance bounds the search from the start
+static const int* g_seed = nullptr;
+static const float* g_seed_xyz = nullptr;      // target points in original order
+void emul_nn_set_seed(const int* seed, const float* target_xyz) { g_seed = seed; g_seed_xyz = target_xyz; }
+
 // the cooperative search of icp_iter_kernel<COOP = true>, one query at a time; bd_init as in er_icp_align_batch
 void emul_nn_coop(void* h, const float* q, int m, float bd_init, int* idx, float* d2) {
   const GridDev& g = ((Grid*)h)->g;
@@ -85,6 +96,13 @@ void emul_nn_coop(void* h, const float* q, int m, float bd_init, int* idx, float
   for (int i = 0; i < m; i++) {
     const float sx = q[3 * (size_t)i], sy = q[3 * (size_t)i + 1], sz = q[3 * (size_t)i + 2];
     unsigned long long key = pack_key(bd_init, kNoMatch);
+    long long n_pts = 0, n_items = 0, n_runs = 0;
+    if (g_seed && g_seed[i] >= 0) {
+      const float* t = g_seed_xyz + 3 * (size_t)g_seed[i];
+      const unsigned long long k2 = nn_key(er_float4{t[0], t[1], t[2], __int_as_float(g_seed[i])}, sx, sy, sz);
+      if (k2 < key) key = k2;
+      n_pts++;
+    }
     const float lx = __fmul_rn(__fsub_rn(sx, g.org[0]), g.inv_cell);
     const float ly = __fmul_rn(__fsub_rn(sy, g.org[1]), g.inv_cell);
     const float lz = __fmul_rn(__fsub_rn(sz, g.org[2]), g.inv_cell);
@@ -94,10 +112,11 @@ void emul_nn_coop(void* h, const float* q, int m, float bd_init, int* idx, float
     if (valid) {
       const int cx = (int)flx, cy = (int)fly, cz = (int)flz;
       const float fx = lx - flx, fy = ly - fly, fz = lz - flz;
-      float bd = bd_init;
+      float bd = __uint_as_float((unsigned)(key >> 32));
       if (cx >= 0 && cx < g.dim[0] && cy >= 0 && cy < g.dim[1] && cz >= 0 && cz < g.dim[2]) {
         const int c = (cx * g.dim[1] + cy) * g.dim[2] + cz;
         nn_scan_key(g, g.cell_start[c], g.cell_start[c + 1], sx, sy, sz, key);
+        n_pts += g.cell_start[c + 1] - g.cell_start[c];
         bd = __uint_as_float((unsigned)(key >> 32));
       }
       int xlo = 0, xhi = 0, ylo = 0, yhi = 0;
@@ -110,6 +129,7 @@ void emul_nn_coop(void* h, const float* q, int m, float bd_init, int* idx, float
         if (!(ox >= xlo && ox <= xhi && oy >= ylo && oy <= yhi)) continue;
         for (int upper = 0; upper < (t == 0 ? 2 : 1); upper++) {
           const int ix = cx + ox, iy = cy + oy;
+          n_items++;
           if (ix < 0 || ix >= g.dim[0] || iy < 0 || iy >= g.dim[1]) continue;
           const float bl = __uint_as_float((unsigned)(key >> 32));
           const float ax = slab_gap(ox, fx, cell, slack), ay = slab_gap(oy, fy, cell, slack);
@@ -133,9 +153,17 @@ void emul_nn_coop(void* h, const float* q, int m, float bd_init, int* idx, float
           if (a0 > a1) continue;
           const int row = (ix * g.dim[1] + iy) * g.dim[2];
           nn_scan_key(g, g.cell_start[row + a0], g.cell_start[row + a1 + 1], sx, sy, sz, key);
+          n_pts += g.cell_start[row + a1 + 1] - g.cell_start[row + a0];
+          n_runs += g.cell_start[row + a1 + 1] > g.cell_start[row + a0];
         }
       }
     }
+#pragma omp atomic
+    g_points += n_pts;
+#pragma omp atomic
+    g_items += n_items;
+#pragma omp atomic
+    g_runs += n_runs;
     const int best = (int)(unsigned)(key & 0xffffffffu);
     idx[i] = best == kNoMatch ? -1 : best;
     d2[i] = __uint_as_float((unsigned)(key >> 32));
