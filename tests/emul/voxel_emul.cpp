@@ -351,4 +351,27 @@ void emul_check_touch(const unsigned short* depth, int cols, int rows, float fx,
   out[0] = n_valid; out[1] = n_exact; out[2] = n_tiles; out[3] = n_uniform; out[4] = bad;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// CIntegrateApp::Reproject for a whole image through reproject_pixel (er_voxel_math.h): z-buffer minimum over the
+// pixels of `depth`, result in `out` (0 where nothing landed), as reproject_kernel + zbuf_to_u16_kernel do.
+// adj = Ti^-1 * T0 * A0^-1 is passed in (the product computes it with er_mat4_inverse / er_mat4_mul on the host).
+// ---------------------------------------------------------------------------------------------------------------
+void emul_reproject(const unsigned short* depth, int cols, int rows, float fx, float fy, float cx, float cy, const double* Ai,
+                    const double* adj, const float* ctr, int res, float length, unsigned short* out) {
+  struct { float fx, fy, cx, cy; int cols, rows; } v{fx, fy, cx, cy, cols, rows};
+  ReprojParams R;
+  for (int i = 0; i < 12; i++) { R.Ai[i] = Ai[i]; R.adj[i] = adj[i]; }
+  R.res = res;
+  R.unit_length = length / (float)res;                           // ControlGrid.cpp:19, er_tsdf.cu reproject_on_device
+  std::vector<unsigned> zbuf((size_t)cols * rows, 0xFFFFFFFFu);
+  for (int pix = 0; pix < cols * rows; pix++) {
+    const unsigned d = depth[pix];
+    if (d == 0) continue;
+    unsigned dd;
+    const int target = reproject_pixel(v, R, ctr, pix % cols, pix / cols, d, dd);
+    if (target >= 0 && dd < zbuf[target]) zbuf[target] = dd;
+  }
+  for (int i = 0; i < cols * rows; i++) out[i] = (zbuf[i] == 0xFFFFFFFFu) ? (unsigned short)0 : (unsigned short)zbuf[i];
+}
+
 }  // extern "C"

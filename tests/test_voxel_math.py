@@ -175,3 +175,35 @@ def test_second_pixel_form_matches_oracle_on_scenes(oracle, emul, bias):
     finally:
         emul.emul_set_rcp_bias(0)
         emul.emul_set_pixel_form(1)
+
+
+# ------------------------------------------------------------------------------------------------ Reproject
+def test_reproject_pixel_matches_oracle(oracle, emul):
+    """CIntegrateApp::Reproject (ControlGrid warp + forward projection + z-buffer minimum): reproject_pixel from the
+    product header, run over whole images on the CPU, against the oracle's Reproject -- the ControlGrid scene of the
+    golden set (all frames, both fragments) and a stronger random lattice displacement."""
+    emul.emul_reproject.argtypes = [C.POINTER(C.c_ushort), C.c_int, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+                                    C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_float), C.c_int, C.c_float,
+                                    C.POINTER(C.c_ushort)]
+    sc = helpers.scene_ctr(num=2, interval=3)
+    traj = helpers.compose_traj(sc["pose_traj"], sc["seg_traj"], sc["interval"], capi.mat4_mul)
+    ovol = oracle.OracleTSDF()
+    rng = np.random.default_rng(5)
+    changed = 0
+    for variant in range(2):
+        for f in range(len(sc["frames"])):
+            chunk = f // sc["interval"]
+            ctr = np.ascontiguousarray(sc["grids"][chunk], dtype=np.float32)
+            if variant == 1:
+                ctr = (ctr + rng.normal(0, 0.004, ctr.shape)).astype(np.float32)      # a rougher lattice
+            Ti, T0, A0, Ai = traj[f], traj[0], sc["seg_traj"][0], sc["seg_traj"][f]
+            want = ovol.reproject(sc["frames"][f], Ti, T0, A0, Ai, ctr, sc["res"], sc["length"])
+            adj = capi.mat4_mul(capi.mat4_mul(capi.mat4_inverse(Ti), T0), capi.mat4_inverse(A0))   # reproject_on_device
+            depth = np.ascontiguousarray(sc["frames"][f], dtype=np.uint16)
+            got = np.zeros_like(depth)
+            emul.emul_reproject(depth.ctypes.data_as(C.POINTER(C.c_ushort)), 640, 480, 525.0, 525.0, 319.5, 239.5,
+                                _dp(np.ascontiguousarray(Ai, dtype=np.float64)), _dp(np.ascontiguousarray(adj, dtype=np.float64)),
+                                _fp(ctr.ravel()), sc["res"], C.c_float(sc["length"]), got.ctypes.data_as(C.POINTER(C.c_ushort)))
+            assert np.array_equal(got, want), "variant %d frame %d: %d pixels differ" % (variant, f, int((got != want).sum()))
+            changed += int((want != depth).sum())
+    assert changed > 100000                      # the warp really moves pixels
