@@ -15,7 +15,10 @@
  * constructTransformationMatrix, default_convergence_criteria.hpp hasConverged, kdtree_flann.hpp with
  * flann::L2_Simple<float>, common/impl/transforms.hpp transformPointCloudWithNormals) from knowledge of those
  * sources; this file is therefore the DEFINITION the CUDA path is held to (tests cross-check its nearest
- * neighbour search against brute force and scipy.spatial.cKDTree and its 6x6 solve against numpy).
+ * neighbour search against brute force and scipy.spatial.cKDTree and its 6x6 solve against numpy).  The Eigen
+ * half of PCL's arithmetic IS pinned: oracle/eigen_check.cpp runs the Eigen 3.1.2 the reference vendors, and
+ * tests/test_oracle_icp.py finds the Matrix4f products restated below bit-identical to it and the 6x6 solve within
+ * 1.6e-10 relative of ATA.inverse() * ATb (no difference left after the narrowing to float).
  *
  * Deliberate choices where PCL/FLANN leave freedom:
  *   - exact 1-NN on xyz with squared distance ((dx*dx + dy*dy) + dz*dz) in float (L2_Simple order); among
@@ -219,6 +222,14 @@ static void transform_points_f(const float *M, float *xyz, int n) {   /* Iterati
     float x = xyz[3 * i], y = xyz[3 * i + 1], z = xyz[3 * i + 2];
     for (int r = 0; r < 3; r++) xyz[3 * i + r] = ((M[r * 4] * x + M[r * 4 + 1] * y) + M[r * 4 + 2] * z) + M[r * 4 + 3] * 1.0f;
   }
+}
+
+/* exported for tests/test_oracle_icp.py, which compares them with the vendored Eigen 3.1.2 (oracle/eigen_check.cpp) */
+void oracle_mat4f_mul(const float *a, const float *b, float *o) { mat4f_mul(a, b, o); }
+void oracle_transform_point_f(const float *M, const float *p, float *o) {
+  float q[3] = {p[0], p[1], p[2]};
+  transform_points_f(M, q, 1);
+  o[0] = q[0]; o[1] = q[1]; o[2] = q[2];
 }
 
 /* ------------------------------------------------------------------ b2/b3: CorresApp.cpp:295-312

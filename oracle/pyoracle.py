@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 REF_INTEGRATE = os.path.join(_HERE, "_ref", "Integrate_ref")
 REF_INTEGRATE_12MM = os.path.join(_HERE, "_ref", "Integrate_ref_12mm")     # unit_length_ patched to 0.012 (Makefile: ref12)
+EIGEN_CHECK = os.path.join(_HERE, "_ref", "libeigen_check.so")              # the reference's vendored Eigen 3.1.2 (Makefile: eigen)
 
 _lib = None
 
@@ -29,6 +30,8 @@ def build(force: bool = False) -> None:
         subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
     if os.path.isdir("/root/reference/Integrate") and (force or not os.path.exists(REF_INTEGRATE_12MM)):
         subprocess.check_call(["make", "-C", _HERE, "-s", "ref12"])
+    if os.path.isdir("/root/reference/FragmentOptimizer/external/Eigen") and (force or not os.path.exists(EIGEN_CHECK)):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "eigen"])
 
 
 def lib():

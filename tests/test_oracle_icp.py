@@ -81,3 +81,71 @@ def test_information_matrix_layout_matches_reference_fixture(oracle, pair):
         assert blk[0, 0] == blk[1, 1] == blk[2, 2] and abs(blk[0, 4] + blk[1, 3]) < 1e-6
         assert abs(blk[0, 5] + blk[2, 3]) < 1e-6 and abs(blk[1, 5] + blk[2, 4]) < 1e-6
     assert np.all(np.diff(pairs[:, 1]) > 0)        # ascending source index (CorresApp.cpp:157)
+
+
+# ------------------------------------------------------------------------------------------------ the real Eigen 3.1.2
+def _eigen(oracle):
+    import ctypes as C
+    if not os.path.exists(oracle.EIGEN_CHECK):
+        pytest.skip("oracle/_ref/libeigen_check.so not built (needs the reference's vendored Eigen at build time)")
+    L = C.CDLL(oracle.EIGEN_CHECK)
+    dp, fp = C.POINTER(C.c_double), C.POINTER(C.c_float)
+    L.eigen_inverse_solve6.argtypes = [dp, dp, dp]
+    L.eigen_mat4f_mul.argtypes = [fp, fp, fp]
+    L.eigen_mat4f_point.argtypes = [fp, fp, fp]
+    return L, dp, fp
+
+
+def test_float_matrix_products_match_the_vendored_eigen_bit_for_bit(oracle):
+    """final = T_inc * final (Matrix4f product) and transformCloud's Matrix4f * (x, y, z, 1): the restated evaluation
+    order ((a0 b0 + a1 b1) + a2 b2) + a3 b3 against Eigen 3.1.2 itself (the library the reference vendors and its
+    Integrate path is compiled with), on rigid transforms and on arbitrary matrices."""
+    import ctypes as C
+    L, dp, fp = _eigen(oracle)
+    O = oracle.lib()
+    O.oracle_mat4f_mul.argtypes = [fp, fp, fp]
+    O.oracle_transform_point_f.argtypes = [fp, fp, fp]
+    rng = np.random.default_rng(8)
+    for k in range(2000):
+        if k % 2:
+            a = synth.make_pose(synth.rot_axis(rng.normal(size=3), rng.uniform(0, 0.1)), rng.normal(0, 0.02, 3)).astype(np.float32)
+            b = synth.make_pose(synth.rot_axis(rng.normal(size=3), rng.uniform(0, 3)), rng.uniform(-3, 3, 3)).astype(np.float32)
+        else:
+            a, b = rng.normal(size=(4, 4)).astype(np.float32), rng.normal(size=(4, 4)).astype(np.float32)
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        o1, o2 = np.empty((4, 4), np.float32), np.empty((4, 4), np.float32)
+        L.eigen_mat4f_mul(a.ctypes.data_as(fp), b.ctypes.data_as(fp), o1.ctypes.data_as(fp))
+        O.oracle_mat4f_mul(a.ctypes.data_as(fp), b.ctypes.data_as(fp), o2.ctypes.data_as(fp))
+        assert np.array_equal(o1.view(np.uint32), o2.view(np.uint32))
+        p = rng.uniform(-3, 3, 3).astype(np.float32)
+        q1, q2 = np.empty(3, np.float32), np.empty(3, np.float32)
+        L.eigen_mat4f_point(b.ctypes.data_as(fp), p.ctypes.data_as(fp), q1.ctypes.data_as(fp))
+        O.oracle_transform_point_f(b.ctypes.data_as(fp), p.ctypes.data_as(fp), q2.ctypes.data_as(fp))
+        assert np.array_equal(q1.view(np.uint32), q2.view(np.uint32))
+
+
+def test_solve6_against_eigen_inverse_times_rhs(oracle, pair):
+    """PCL solves the 6x6 normal equations as ATA.inverse() * ATb; the oracle (and the kernel) eliminate with partial
+    pivoting.  On normal equations of real point-to-plane rows the two agree to ~1e-12 relative, far below the float
+    the solution is narrowed to when the transform is built: the float transforms built from both are compared too."""
+    L, dp, fp = _eigen(oracle)
+    tgt, src = pair
+    rng = np.random.default_rng(9)
+    worst, float_diffs, total = 0.0, 0, 0
+    for _ in range(200):
+        k = rng.choice(len(src), 3000, replace=False)
+        s = src.xyz[k].astype(np.float64) + rng.normal(0, 0.002, (3000, 3))
+        n = tgt.nrm[rng.choice(len(tgt), 3000)].astype(np.float64)
+        d = rng.normal(0, 0.003, 3000)
+        J = np.concatenate([np.cross(s, n), n], axis=1)
+        A = np.ascontiguousarray(J.T @ J)
+        b = np.ascontiguousarray(J.T @ d)
+        x1 = np.empty(6)
+        L.eigen_inverse_solve6(A.ctypes.data_as(dp), b.ctypes.data_as(dp), x1.ctypes.data_as(dp))
+        x2 = oracle.solve6(A, b)
+        rel = np.max(np.abs(x1 - x2) / (np.abs(x2) + 1e-12))
+        worst = max(worst, rel)
+        float_diffs += int(np.sum(x1.astype(np.float32) != x2.astype(np.float32)))
+        total += 6
+    assert worst < 1e-8, worst
+    assert float_diffs <= total // 100, (float_diffs, total)       # the float narrowing hides the difference almost always
