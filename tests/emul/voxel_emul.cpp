@@ -374,4 +374,43 @@ void emul_reproject(const unsigned short* depth, int cols, int rows, float fx, f
   for (int i = 0; i < cols * rows; i++) out[i] = (zbuf[i] == 0xFFFFFFFFu) ? (unsigned short)0 : (unsigned short)zbuf[i];
 }
 
+// exploration helper: classes (0 SKIP, 1 ONE, 2 FULL) of the 4096 sub-bricks of one block for one frame, as
+// classify_kernel assigns them (index = brick * 8 + q); tight = 1 uses classify_ball<true>
+void emul_classify_block(const float* scaled, int cols, int rows, float fx, float fy, float cx, float cy, double ul_d, double trunc,
+                         const double* T, const double* Tinv, int key, int tight, unsigned char* cls_out) {
+  ClassifyConsts v;
+  v.fx = fx; v.fy = fy; v.cx = cx; v.cy = cy; v.cols = cols; v.rows = rows; v.trunc_d = trunc;
+  er_voxel_thresholds(trunc, &v.thr_neg, &v.thr_one, &v.trunc_eps);
+  v.ntx = (cols + kErTile - 1) / kErTile;
+  const int nty = (rows + kErTile - 1) / kErTile;
+  static thread_local const float* cached = nullptr;
+  static thread_local std::vector<er_tile_t> l16, l8, l4;
+  if (cached != scaled) {
+    build_level(scaled, cols, rows, v.ntx, nty, 16, l16);
+    build_level(scaled, cols, rows, v.ntx, nty, 8, l8);
+    build_level(scaled, cols, rows, v.ntx, nty, 4, l4);
+    cached = scaled;
+  }
+  v.tiles = l16.data(); v.tiles8 = l8.data(); v.tiles4 = l4.data();
+  float P[15];
+  for (int i = 0; i < 12; i++) P[i] = (float)Tinv[i];
+  P[12] = (float)T[3]; P[13] = (float)T[7]; P[14] = (float)T[11];
+  const float ul = (float)ul_d;
+  const float R8 = (float)(1.7320508 * 3.5 * ul_d) + 1e-4f, R4 = (float)(1.7320508 * 1.5 * ul_d) + 1e-4f;
+  const int xi = key / (kGridDim * kGridDim), yi = (key / kGridDim) % kGridDim, zi = key % kGridDim;
+  for (int brick = 0; brick < 512; brick++) {
+    const float bx = (float)((xi - kGridHalf) * kRes + (brick >> 6) * 8);
+    const float by = (float)((yi - kGridHalf) * kRes + ((brick >> 3) & 7) * 8);
+    const float bz = (float)((zi - kGridHalf) * kRes + (brick & 7) * 8);
+    const int c8 = tight ? classify_ball<true>(v, P, 0, (bx + 3.5f) * ul, (by + 3.5f) * ul, (bz + 3.5f) * ul, R8, 3.5f * ul)
+                         : classify_ball(v, P, 0, (bx + 3.5f) * ul, (by + 3.5f) * ul, (bz + 3.5f) * ul, R8);
+    for (int q = 0; q < 8; q++) {
+      const float qx = (bx + 1.5f + 4.0f * ((q >> 2) & 1)) * ul, qy = (by + 1.5f + 4.0f * ((q >> 1) & 1)) * ul,
+                  qz = (bz + 1.5f + 4.0f * (q & 1)) * ul;
+      cls_out[brick * 8 + q] = (unsigned char)((c8 != 2) ? c8
+                               : (tight ? classify_ball<true>(v, P, 0, qx, qy, qz, R4, 1.5f * ul) : classify_ball(v, P, 0, qx, qy, qz, R4)));
+    }
+  }
+}
+
 }  // extern "C"
