@@ -8,6 +8,11 @@ own classify_ball (tests/emul/voxel_emul.cpp -> emul_classify_block); a sub-bric
   dynamic   a CTA takes a whole brick; its 8 sub-bricks are tasks pulled by the 4 warps in natural order
   LPT       the same, tasks in order of decreasing cost (-DER_INT_BRICK_LPT)
   8 warps   a whole brick on 8 warps, one sub-brick each
+and, as list scheduling of the whole launch on 1184 resident CTAs (resp. 4736 warps) treated as independent equal-speed
+machines -- which they are not quite: CTAs of one SM share its issue slots -- the kernel's makespan for
+  today     half-brick units handed to CTAs, heavy bricks first
+  brick-LPT whole-brick units handed to CTAs (-DER_INT_BRICK_LPT)
+  tasks     sub-brick tasks handed to warps, 1 / 2 / 4 per fetch (-DER_INT_TASKS), heavy sub-bricks first
 
     python tools/simulate_integrate_balance.py
 """
@@ -83,6 +88,43 @@ def simulate(full, one, a=300.0, b=25.0, c=60.0):
     return tot, cur, dyn, lpt, w8, nbr
 
 
+def makespan(order, machines, chunk=1):
+    import heapq
+    h = [0.0] * machines
+    heapq.heapify(h)
+    for i in range(0, len(order), chunk):
+        heapq.heappush(h, heapq.heappop(h) + sum(order[i:i + chunk]))
+    return max(h)
+
+
+def global_model(full, one, a=300.0, b=25.0, c=60.0, ctas=1184, warps=4):
+    rng = np.random.default_rng(0)
+    cur = [[], []]
+    lpt = [[], []]
+    task = [[], []]
+    for k in full:
+        F, O = full[k].reshape(512, 8), one[k].reshape(512, 8)
+        act = (F + O) > 0
+        cost = np.where(act, a * F + b * O + c, 0.0)
+        for br in np.where(act.any(axis=1))[0]:
+            cs = cost[br]
+            light = int(F[br].sum() < 32)                       # classify_kernel: heavy bricks to the front
+            cur[light] += [cs[:4].max(), cs[4:].max()]
+            m = np.zeros(warps)
+            for t in sorted(cs, reverse=True):
+                m[np.argmin(m)] += t
+            lpt[light].append(m.max())
+            for q in range(8):
+                if act[br, q]:
+                    task[int(F[br, q] < 16)].append(cs[q])
+    order = lambda two: list(rng.permutation(two[0])) + list(rng.permutation(two[1]))     # noqa: E731  arrival order inside a class
+    total = sum(task[0]) + sum(task[1])
+    res = {"ideal": total / (ctas * warps), "today": makespan(order(cur), ctas), "brick-LPT": makespan(order(lpt), ctas)}
+    for ch in (1, 2, 4):
+        res["tasks/%d" % ch] = makespan(order(task), ctas * warps, ch)
+    return res
+
+
 def main():
     pyoracle.build()
     L, fp, dp = load()
@@ -98,6 +140,11 @@ def main():
               "dynamic %.1f %%, LPT %.1f %%, 8 warps %.1f %% | summed step time relative to today's default: current %.3f, LPT %.3f"
               % ("box-based" if tight else "ball-based", nbr, tot, 100 * tot / (4 * cur), 100 * tot / (4 * dyn), 100 * tot / (4 * lpt),
                  100 * tot / (8 * w8), cur / base, lpt / base))
+        g = global_model(full, one)
+        if tight == 0:
+            today = g["today"]
+        print("    launch makespan model (relative to today's default): " +
+              ", ".join("%s %.2f" % (k, v / today) for k, v in g.items()))
 
 
 if __name__ == "__main__":
