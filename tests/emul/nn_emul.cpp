@@ -83,6 +83,8 @@ void emul_nn_counters(long long* out, int reset) {
   if (reset) g_points = g_items = g_runs = 0;
 }
 // exploration: seed[i] >= 0 names a target point (original index) whose distance bounds the search from the start
+static int* g_trace = nullptr;                 // per query: centre-cell points, xlo, xhi, ylo, yhi, runs scanned, points in runs
+void emul_nn_set_trace(int* trace7) { g_trace = trace7; }
 static const int* g_seed = nullptr;
 static const float* g_seed_xyz = nullptr;      // target points in original order
 void emul_nn_set_seed(const int* seed, const float* target_xyz) { g_seed = seed; g_seed_xyz = target_xyz; }
@@ -117,6 +119,7 @@ void emul_nn_coop(void* h, const float* q, int m, float bd_init, int* idx, float
         const int c = (cx * g.dim[1] + cy) * g.dim[2] + cz;
         nn_scan_key(g, g.cell_start[c], g.cell_start[c + 1], sx, sy, sz, key);
         n_pts += g.cell_start[c + 1] - g.cell_start[c];
+        if (g_trace) g_trace[7 * (size_t)i] = g.cell_start[c + 1] - g.cell_start[c];
         bd = __uint_as_float((unsigned)(key >> 32));
       }
       int xlo = 0, xhi = 0, ylo = 0, yhi = 0;
@@ -124,6 +127,7 @@ void emul_nn_coop(void* h, const float* q, int m, float bd_init, int* idx, float
       for (int o = 1; o <= K; o++) { const float a = slab_gap(-o, fx, cell, slack); if (a * a > bd) break; xlo = -o; }
       for (int o = 1; o <= K; o++) { const float a = slab_gap(o, fy, cell, slack); if (a * a > bd) break; yhi = o; }
       for (int o = 1; o <= K; o++) { const float a = slab_gap(-o, fy, cell, slack); if (a * a > bd) break; ylo = -o; }
+      if (g_trace) { int* tr = g_trace + 7 * (size_t)i; tr[1] = xlo; tr[2] = xhi; tr[3] = ylo; tr[4] = yhi; }
       for (int t = 0; t < 25; t++) {
         const int ox = kColumnOrder[t][0], oy = kColumnOrder[t][1];
         if (!(ox >= xlo && ox <= xhi && oy >= ylo && oy <= yhi)) continue;
@@ -155,6 +159,10 @@ void emul_nn_coop(void* h, const float* q, int m, float bd_init, int* idx, float
           nn_scan_key(g, g.cell_start[row + a0], g.cell_start[row + a1 + 1], sx, sy, sz, key);
           n_pts += g.cell_start[row + a1 + 1] - g.cell_start[row + a0];
           n_runs += g.cell_start[row + a1 + 1] > g.cell_start[row + a0];
+          if (g_trace && g.cell_start[row + a1 + 1] > g.cell_start[row + a0]) {
+            g_trace[7 * (size_t)i + 5]++;
+            g_trace[7 * (size_t)i + 6] += g.cell_start[row + a1 + 1] - g.cell_start[row + a0];
+          }
         }
       }
     }
