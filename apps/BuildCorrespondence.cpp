@@ -67,7 +67,49 @@ struct CorresApp {
   std::vector<er_cloud*> clouds;                       // on `device`: gate, ICP share, correspondences
   std::vector<std::vector<er_cloud*>> replica;         // replica[k][i]: fragment i on extra_devices[k] (ICP share only)
   long icp_pairs = 0, icp_iterations = 0;
-  double icp_ms = 0;
+  double icp_ms = 0, gate_ms = 0, corres_ms = 0, write_ms = 0, load_ms = 0, upload_ms = 0;
+
+  // Runs fn(k, share, clouds-on-device-k, error) for device k's round-robin share of a list of n independent items, one
+  // host thread per device (the reference's pair loops are OpenMP loops over independent pairs, CorresApp.cpp:121,220).
+  template <class Fn>
+  bool on_devices(int n, Fn fn, std::string& err) {
+    const int ndev = 1 + (int)extra_devices.size();
+    std::vector<std::string> errs((size_t)ndev);
+#pragma omp parallel for num_threads(ndev) schedule(static, 1)
+    for (int k = 0; k < ndev; k++) {
+      std::vector<int> sel;
+      for (int p = k; p < n; p += ndev) sel.push_back(p);
+      if (sel.empty()) continue;
+      er_cloud* const* cl = (k == 0) ? clouds.data() : replica[(size_t)k - 1].data();
+      fn(k, sel, cl, errs[(size_t)k]);                 // (the library's error text is per host thread: fn copies it)
+    }
+    for (int k = 0; k < ndev; k++)
+      if (!errs[(size_t)k].empty()) {
+        err = "device " + std::to_string(k == 0 ? device : extra_devices[(size_t)k - 1]) + ": " + errs[(size_t)k];
+        return false;
+      }
+    return true;
+  }
+
+  // "<target index> <source index>" per line (CorresApp.cpp:175-184), formatted by hand into one buffer: fprintf per
+  // line dominates the run time of the correspondence pass otherwise
+  static void write_corres_file(const char* fn, const std::vector<int32_t>& rows) {
+    FILE* f = std::fopen(fn, "w");
+    if (!f) return;
+    std::string buf;
+    buf.reserve(rows.size() * 8 + 16);
+    char tmp[32];
+    auto put = [&](int v) {
+      int n = 0;
+      unsigned u = v < 0 ? 0u - (unsigned)v : (unsigned)v;
+      do { tmp[n++] = (char)('0' + u % 10); u /= 10; } while (u);
+      if (v < 0) buf.push_back('-');
+      while (n) buf.push_back(tmp[--n]);
+    };
+    for (size_t k = 0; k + 1 < rows.size(); k += 2) { put(rows[k]); buf.push_back(' '); put(rows[k + 1]); buf.push_back('\n'); }
+    std::fwrite(buf.data(), 1, buf.size(), f);
+    std::fclose(f);
+  }
 
   ~CorresApp() {
     for (auto* c : clouds) er_cloud_free(c);
@@ -145,6 +187,7 @@ struct CorresApp {
     clouds.assign(num, nullptr);
     if (bbox_length > 0.0) std::printf("BBox prune enabled : %.6f\n", bbox_length);
     bool ok = true;
+    const auto tl0 = std::chrono::steady_clock::now();
 #pragma omp parallel for num_threads(8) schedule(dynamic)
     for (int i = 0; i < num; i++) {
       char fn[1024];
@@ -168,6 +211,8 @@ struct CorresApp {
         }
       }
     }
+    const auto tl1 = std::chrono::steady_clock::now();
+    load_ms = std::chrono::duration<double, std::milli>(tl1 - tl0).count();
     const double cell = std::max(reg_dist, dist_thresh);
 #pragma omp parallel for num_threads(8) schedule(dynamic)
     for (int i = 0; i < num; i++) {
@@ -189,6 +234,7 @@ struct CorresApp {
         }
       }
     }
+    upload_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tl1).count();
     return ok;
   }
 
@@ -223,6 +269,42 @@ struct CorresApp {
     const int total = (int)corres_traj.data.size();
     int nprocessed = 0;
     std::vector<int> todo;           // accepted pairs that need ICP
+    // the gate of every candidate (CorresApp.cpp:250-264) in one batched pass per device instead of one blocking call
+    // per pair; the decisions below run in list order on its counts, as the reference's pair loop prints them
+    std::vector<int> cand, gate_cnt((size_t)total, 0);
+    for (int i = 0; i < total; i++) {
+      const FramedTransformation& d = corres_traj.data[i];
+      if (!blacklisted(d) && d.frame != -1) cand.push_back(i);
+    }
+    {
+      const auto tg0 = std::chrono::steady_clock::now();
+      const int nc = (int)cand.size();
+      std::vector<int> ti(nc), si(nc), cnt(nc);
+      std::vector<double> Tc(16 * (size_t)nc);
+      for (int p = 0; p < nc; p++) {
+        const FramedTransformation& d = corres_traj.data[cand[p]];
+        ti[p] = d.id1; si[p] = d.id2;
+        std::memcpy(&Tc[16 * (size_t)p], d.T, sizeof d.T);
+      }
+      std::string err;
+      if (!on_devices(nc, [&](int k, const std::vector<int>& sel, er_cloud* const* cl, std::string& e) {
+            const int m = (int)sel.size();
+            std::vector<int> t2(m), s2(m), c2(m);
+            std::vector<double> T2(16 * (size_t)m);
+            for (int q = 0; q < m; q++) {
+              t2[q] = ti[sel[q]]; s2[q] = si[sel[q]];
+              std::memcpy(&T2[16 * (size_t)q], &Tc[16 * (size_t)sel[q]], 16 * sizeof(double));
+            }
+            if (er_icp_count_inliers_batch(cl, num, t2.data(), s2.data(), m, T2.data(), reg_dist, c2.data())) { e = er_last_error(); return; }
+            for (int q = 0; q < m; q++) cnt[sel[q]] = c2[q];
+            (void)k;
+          }, err)) {
+        std::cerr << "er_icp_count_inliers_batch: " << err << std::endl;
+        return false;
+      }
+      for (int p = 0; p < nc; p++) gate_cnt[(size_t)cand[p]] = cnt[p];
+      gate_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tg0).count();
+    }
     for (int i = 0; i < total; i++) {
       FramedTransformation& d = corres_traj.data[i];
       if (blacklisted(d)) {
@@ -234,11 +316,7 @@ struct CorresApp {
       }
       if (d.frame == -1) { nprocessed++; continue; }            // means reject
       std::printf("Align pair <%d, %d> ... \n", d.id1, d.id2);
-      int cnt = 0;
-      if (er_icp_count_inliers(clouds[d.id1], clouds[d.id2], d.T, reg_dist, &cnt)) {
-        std::cerr << "er_icp_count_inliers: " << er_last_error() << std::endl;
-        return false;
-      }
+      const int cnt = gate_cnt[(size_t)i];
       const size_t n0 = pointclouds[d.id1].size(), n1 = pointclouds[d.id2].size();
       const double r1 = (double)cnt / (double)n0, r2 = (double)cnt / (double)n1;
       std::printf("    <%d, %d> : %d inliers with ratio %.2f(%d) and %.2f(%d) ... ", d.id1, d.id2, cnt, r1, (int)n0, r2, (int)n1);
@@ -277,41 +355,34 @@ struct CorresApp {
     const auto t0 = std::chrono::steady_clock::now();
     // pairs are independent (CorresApp.cpp:220 runs them from an OpenMP loop): share k of the list goes to device k,
     // one host thread per device, results land in the slots of the original list -- no exchange between devices
-    const int ndev = 1 + (int)extra_devices.size();
-    std::vector<std::string> errs((size_t)ndev);
-#pragma omp parallel for num_threads(ndev) schedule(static, 1)
-    for (int k = 0; k < ndev; k++) {
-      std::vector<int> sel;
-      for (int p = k; p < np; p += ndev) sel.push_back(p);
-      const int m = (int)sel.size();
-      if (m == 0) continue;
-      std::vector<int> t2(m), s2(m), it2(m);
-      std::vector<double> Ti2(16 * (size_t)m), To2(16 * (size_t)m), f2(m);
-      for (int q = 0; q < m; q++) {
-        t2[q] = ti[sel[q]]; s2[q] = si[sel[q]];
-        std::memcpy(&Ti2[16 * (size_t)q], &Tin[16 * (size_t)sel[q]], 16 * sizeof(double));
-      }
-      er_cloud* const* cl = (k == 0) ? clouds.data() : replica[(size_t)k - 1].data();
-      if (er_icp_align_batch(cl, num, t2.data(), s2.data(), m, Ti2.data(), reg_dist, 20, 1e-6, fixed_iters ? 1 : 0, To2.data(),
-                             it2.data(), f2.data())) {
-        errs[(size_t)k] = er_last_error();          // the error text is per host thread
-        continue;
-      }
-      for (int q = 0; q < m; q++) {
-        std::memcpy(&Tout[16 * (size_t)sel[q]], &To2[16 * (size_t)q], 16 * sizeof(double));
-        iters[sel[q]] = it2[q];
-        fit[sel[q]] = f2[q];
-      }
-    }
-    for (int k = 0; k < ndev; k++)
-      if (!errs[(size_t)k].empty()) {
-        std::cerr << "er_icp_align_batch (device " << (k == 0 ? device : extra_devices[(size_t)k - 1]) << "): " << errs[(size_t)k] << std::endl;
+    {
+      std::string err;
+      if (!on_devices(np, [&](int, const std::vector<int>& sel, er_cloud* const* cl, std::string& e) {
+            const int m = (int)sel.size();
+            std::vector<int> t2(m), s2(m), it2(m);
+            std::vector<double> Ti2(16 * (size_t)m), To2(16 * (size_t)m), f2(m);
+            for (int q = 0; q < m; q++) {
+              t2[q] = ti[sel[q]]; s2[q] = si[sel[q]];
+              std::memcpy(&Ti2[16 * (size_t)q], &Tin[16 * (size_t)sel[q]], 16 * sizeof(double));
+            }
+            if (er_icp_align_batch(cl, num, t2.data(), s2.data(), m, Ti2.data(), reg_dist, 20, 1e-6, fixed_iters ? 1 : 0, To2.data(),
+                                   it2.data(), f2.data())) { e = er_last_error(); return; }
+            for (int q = 0; q < m; q++) {
+              std::memcpy(&Tout[16 * (size_t)sel[q]], &To2[16 * (size_t)q], 16 * sizeof(double));
+              iters[sel[q]] = it2[q];
+              fit[sel[q]] = f2[q];
+            }
+          }, err)) {
+        std::cerr << "er_icp_align_batch: " << err << std::endl;
         return false;
       }
+    }
     icp_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     for (int p = 0; p < np; p++) {
       FramedTransformation& d = corres_traj.data[todo[p]];
-      std::printf("    <%d, %d> : ICP fitness score is %.6f\n", d.id1, d.id2, fit[p]);
+      // (the reference prints pcl's getFitnessScore() here -- mean NN distance^2 of ALL source points under the final pose;
+      // this is the mean over the last iteration's correspondences, hence the different label)
+      std::printf("    <%d, %d> : ICP correspondence MSE is %.6f\n", d.id1, d.id2, fit[p]);
       std::printf("    Matrix from : \n");
       for (int r = 0; r < 4; r++) std::printf("%g %g %g %g\n", d.T[r * 4], d.T[r * 4 + 1], d.T[r * 4 + 2], d.T[r * 4 + 3]);
       std::memcpy(d.T, &Tout[16 * (size_t)p], sizeof d.T);
@@ -335,40 +406,84 @@ struct CorresApp {
         corres_info.data.push_back(fi);
       }
     }
-    std::vector<int32_t> pairs;
+    // the pair loop of CorresApp.cpp:121 in batches: one launch sequence and one synchronisation per batch on each
+    // device, then the corres_<i>_<j>.txt files of the batch written from 8 host threads
+    std::vector<int> cand;
     for (int i = 0; i < (int)corres_traj.data.size(); i++) {
-      FramedTransformation& d = corres_traj.data[i];
-      if (blacklisted(d)) continue;
-      if (d.frame == -1) continue;                              // means reject
-      std::printf("Processing pair <%d, %d>\n", d.id1, d.id2);
-      const size_t cap = pointclouds[d.id2].size();
-      pairs.resize(2 * (cap ? cap : 1));
-      size_t n = 0;
-      double info[36];
-      if (er_icp_correspondences(clouds[d.id1], clouds[d.id2], d.T, dist_thresh, normal_thresh, pairs.data(), cap, &n,
-                                 output_information ? info : nullptr)) {
-        std::cerr << "er_icp_correspondences: " << er_last_error() << std::endl;
+      const FramedTransformation& d = corres_traj.data[i];
+      if (!blacklisted(d) && d.frame != -1) cand.push_back(i);              // -1 means reject
+    }
+    const size_t kBatchRows = 24u << 20;                                    // rows (source points) per batch: 192 MB of pairs
+    const int ndev = 1 + (int)extra_devices.size();
+    for (size_t c0 = 0; c0 < cand.size();) {
+      size_t c1 = c0, rows = 0;
+      while (c1 < cand.size() && (c1 == c0 || rows + pointclouds[corres_traj.data[cand[c1]].id2].size() <= kBatchRows * (size_t)ndev)) {
+        rows += pointclouds[corres_traj.data[cand[c1]].id2].size();
+        c1++;
+      }
+      const int nb = (int)(c1 - c0);
+      std::vector<int> ti(nb), si(nb);
+      std::vector<double> Tc(16 * (size_t)nb), info(output_information ? 36 * (size_t)nb : 0);
+      std::vector<std::vector<int32_t>> rows_of((size_t)nb);
+      for (int p = 0; p < nb; p++) {
+        const FramedTransformation& d = corres_traj.data[cand[c0 + p]];
+        ti[p] = d.id1; si[p] = d.id2;
+        std::memcpy(&Tc[16 * (size_t)p], d.T, sizeof d.T);
+      }
+      const auto tc0 = std::chrono::steady_clock::now();
+      std::string err;
+      if (!on_devices(nb, [&](int, const std::vector<int>& sel, er_cloud* const* cl, std::string& e) {
+            const int m = (int)sel.size();
+            std::vector<int> t2(m), s2(m);
+            std::vector<double> T2(16 * (size_t)m), I2(output_information ? 36 * (size_t)m : 0);
+            size_t cap = 0;
+            for (int q = 0; q < m; q++) {
+              t2[q] = ti[sel[q]]; s2[q] = si[sel[q]];
+              std::memcpy(&T2[16 * (size_t)q], &Tc[16 * (size_t)sel[q]], 16 * sizeof(double));
+              cap += pointclouds[si[sel[q]]].size();
+            }
+            std::vector<int32_t> buf(2 * (cap ? cap : 1));
+            std::vector<size_t> start((size_t)m + 1);
+            if (er_icp_correspondences_batch(cl, num, t2.data(), s2.data(), m, T2.data(), dist_thresh, normal_thresh, buf.data(), cap,
+                                             start.data(), output_information ? I2.data() : nullptr)) { e = er_last_error(); return; }
+            for (int q = 0; q < m; q++) {
+              rows_of[(size_t)sel[q]].assign(buf.begin() + 2 * start[q], buf.begin() + 2 * start[q + 1]);
+              if (output_information) std::memcpy(&info[36 * (size_t)sel[q]], &I2[36 * (size_t)q], 36 * sizeof(double));
+            }
+          }, err)) {
+        std::cerr << "er_icp_correspondences_batch: " << err << std::endl;
         return false;
       }
-      std::printf("    <%d, %d> : Corresponce number is %d, ratio is %.2f(%d)\n", d.id1, d.id2, (int)n, (double)n / (double)d.frame, d.frame);
-      if ((double)n / (double)d.frame < 0.5) {
-        std::fprintf(stderr, "    <%d, %d> : Reduced too much!!\n", d.id1, d.id2);
-        d.frame = (reg_num > 0) ? -1 : (int)n;
-      } else {
-        d.frame = (int)n;
-      }
-      if (save_corres) {
-        char fn[1024];
-        std::snprintf(fn, sizeof fn, "%scorres_%d_%d.txt", dir_name.c_str(), d.id1, d.id2);
-        if (FILE* f = std::fopen(fn, "w")) {
-          for (size_t k = 0; k < n; k++) std::fprintf(f, "%d %d\n", pairs[2 * k], pairs[2 * k + 1]);
-          std::fclose(f);
+      corres_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tc0).count();
+      for (int p = 0; p < nb; p++) {
+        const int i = cand[c0 + p];
+        FramedTransformation& d = corres_traj.data[i];
+        const size_t n = rows_of[(size_t)p].size() / 2;
+        std::printf("Processing pair <%d, %d>\n", d.id1, d.id2);
+        std::printf("    <%d, %d> : Corresponce number is %d, ratio is %.2f(%d)\n", d.id1, d.id2, (int)n, (double)n / (double)d.frame, d.frame);
+        if ((double)n / (double)d.frame < 0.5) {
+          std::fprintf(stderr, "    <%d, %d> : Reduced too much!!\n", d.id1, d.id2);
+          d.frame = (reg_num > 0) ? -1 : (int)n;
+        } else {
+          d.frame = (int)n;
+        }
+        if (output_information) {
+          corres_info.data[i].frame = d.frame;
+          std::memcpy(corres_info.data[i].I, &info[36 * (size_t)p], 36 * sizeof(double));
         }
       }
-      if (output_information) {
-        corres_info.data[i].frame = d.frame;
-        std::memcpy(corres_info.data[i].I, info, sizeof info);
+      if (save_corres) {
+        const auto tw0 = std::chrono::steady_clock::now();
+#pragma omp parallel for num_threads(8) schedule(dynamic)
+        for (int p = 0; p < nb; p++) {
+          const FramedTransformation& d = corres_traj.data[cand[c0 + p]];
+          char fn[1024];
+          std::snprintf(fn, sizeof fn, "%scorres_%d_%d.txt", dir_name.c_str(), d.id1, d.id2);
+          write_corres_file(fn, rows_of[(size_t)p]);
+        }
+        write_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
       }
+      c0 = c1;
     }
     return true;
   }
@@ -434,9 +549,11 @@ int main(int argc, char* argv[]) {
     std::cerr << "Registration All took " << std::chrono::duration<double, std::milli>(t2 - t0).count() << "ms." << std::endl;
     if (!bench_json.empty()) {
       if (FILE* f = std::fopen(bench_json.c_str(), "w")) {
-        std::fprintf(f, "{\"pairs\": %d, \"icp_pairs\": %ld, \"icp_iterations\": %ld, \"icp_ms\": %.3f, \"total_ms\": %.3f}\n",
-                     (int)app.corres_traj.data.size(), app.icp_pairs, app.icp_iterations, app.icp_ms,
-                     std::chrono::duration<double, std::milli>(t2 - t0).count());
+        std::fprintf(f, "{\"pairs\": %d, \"icp_pairs\": %ld, \"icp_iterations\": %ld, \"load_ms\": %.3f, \"upload_ms\": %.3f, "
+                        "\"gate_ms\": %.3f, \"icp_ms\": %.3f, \"corres_ms\": %.3f, \"write_ms\": %.3f, \"total_ms\": %.3f, \"devices\": %d}\n",
+                     (int)app.corres_traj.data.size(), app.icp_pairs, app.icp_iterations, app.load_ms, app.upload_ms, app.gate_ms,
+                     app.icp_ms, app.corres_ms, app.write_ms, std::chrono::duration<double, std::milli>(t2 - t0).count(),
+                     1 + (int)app.extra_devices.size());
         std::fclose(f);
       }
     }

@@ -65,6 +65,7 @@ struct App {
   int frame_id = 0;
   bool exit_ = false;
   long processed = 0;
+  double read_ms = 0;
 
   bool fail(const char* what) {
     std::cerr << what << ": " << er_last_error() << std::endl;
@@ -133,18 +134,28 @@ struct App {
   bool run(DepthStream& src) {
     const size_t npix = (size_t)cols * rows;
     const int chunk_frames = 32;
-    std::vector<uint16_t> buf(npix * chunk_frames), batch(npix * chunk_frames);
+    // two page-locked chunk buffers (er_host_alloc): the stream is read straight into them and handed to the library
+    // without another copy; while the devices still copy chunk n out of one buffer the next read fills the other
+    uint16_t* bufs[2] = {(uint16_t*)er_host_alloc(sizeof(uint16_t) * npix * chunk_frames),
+                         (uint16_t*)er_host_alloc(sizeof(uint16_t) * npix * chunk_frames)};
+    struct Free { uint16_t** b; ~Free() { er_host_free(b[0]); er_host_free(b[1]); } } free_bufs{bufs};
+    if (!bufs[0] || !bufs[1]) return fail("er_host_alloc");
     std::vector<double> poses(16 * chunk_frames), segs(16 * chunk_frames);
     std::vector<int> chunks(chunk_frames);
+    int which = 0;
     while (!exit_) {
-      const int got = src.read(buf.data(), chunk_frames);
+      uint16_t* buf = bufs[which];
+      which ^= 1;
+      const auto tr0 = std::chrono::steady_clock::now();
+      const int got = src.read(buf, chunk_frames);
+      read_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count();
       if (got == 0) break;                                    // end of stream
       int nb = 0;
       for (int i = 0; i < got && !exit_; i++) {
         frame_id++;                                           // FrameID is 1-based (IntegrateApp.cpp:185)
         if (!gate(frame_id)) continue;
         const double* T = traj.data[frame_id - 1].T;
-        std::memcpy(batch.data() + npix * nb, buf.data() + npix * i, sizeof(uint16_t) * npix);
+        if (nb != i) std::memmove(buf + npix * nb, buf + npix * i, sizeof(uint16_t) * npix);   // close the gap of skipped frames
         std::memcpy(poses.data() + 16 * nb, T, sizeof(double) * 16);
         if (ctr_num > 0) {                                    // Reproject() inputs of this frame (IntegrateApp.cpp:241-242)
           std::memcpy(segs.data() + 16 * nb, seg_traj.data[frame_id - 1].T, sizeof(double) * 16);
@@ -154,17 +165,18 @@ struct App {
         processed++;
       }
       if (nb > 0) {
-        // every device integrates the same frames into its own share of the blocks (one host thread per device)
+        // every device integrates the same frames into its own share of the blocks (one host thread per device); a pool
+        // or work-list overflow of an earlier chunk comes back from this call (ER_ERR_CAPACITY) and ends the run
         const int ndev = (int)vols.size();
         std::vector<std::string> errs((size_t)ndev);
 #pragma omp parallel for num_threads(ndev) schedule(static, 1)
         for (int k = 0; k < ndev; k++) {
           int rc;
           if (ctr_num > 0)
-            rc = er_tsdf_integrate_ctr_batch(vols[k], batch.data(), poses.data(), traj.data[0].T, seg_traj.data[0].T, segs.data(),
+            rc = er_tsdf_integrate_ctr_batch(vols[k], buf, poses.data(), traj.data[0].T, seg_traj.data[0].T, segs.data(),
                                              chunks.data(), nb);
           else
-            rc = er_tsdf_integrate_batch(vols[k], batch.data(), poses.data(), nb);
+            rc = er_tsdf_integrate_batch(vols[k], buf, poses.data(), nb);
           if (rc) errs[(size_t)k] = er_last_error();       // the error text is per host thread
         }
         for (int k = 0; k < ndev; k++)
@@ -253,8 +265,9 @@ int main(int argc, char* argv[]) {
   std::cerr << "Integrate All took " << ms(t1, t3) << "ms." << std::endl;
   if (!app.bench_json.empty()) {
     if (FILE* f = std::fopen(app.bench_json.c_str(), "w")) {
-      std::fprintf(f, "{\"frames_integrated\": %ld, \"init_ms\": %.3f, \"integrate_ms\": %.3f, \"save_ms\": %.3f}\n",
-                   app.processed, ms(t0, t1), ms(t1, t2), ms(t2, t3));
+      std::fprintf(f, "{\"frames_integrated\": %ld, \"init_ms\": %.3f, \"integrate_ms\": %.3f, \"read_ms\": %.3f, \"save_ms\": %.3f, "
+                      "\"devices\": %d}\n",
+                   app.processed, ms(t0, t1), ms(t1, t2), app.read_ms, ms(t2, t3), (int)app.vols.size());
       std::fclose(f);
     }
   }

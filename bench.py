@@ -1,24 +1,32 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200-native hot paths (contract: see the task brief).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--metric tsdf|icp]
 
-Metric (BASELINE.json): depth frames/s integrated into a 512^3 TSDF (configs[1]: 1000 synthetic 640x480
-frames, rigid trajectory, 512^3 = 8^3 blocks of 64^3 voxels @ 3/512 m, one B200).  A "step" is one pass over
-that sequence: --frames-per-step (default: all 1000) consecutive frames handed to the library in one call.
+Metric (BASELINE.json, first half): depth frames/s integrated into a 512^3 TSDF (configs[1]: 1000 synthetic 640x480
+frames, rigid trajectory, 512^3 = 8^3 blocks of 64^3 voxels @ 3/512 m).  A "step" is one pass over that sequence:
+--frames-per-step (default: all 1000) consecutive frames handed to the library in one call.
 
-  value       frames/s with the frames already resident in HBM (er_tsdf_integrate_device)
-  e2e         frames/s through the C-ABI with HOST buffers: pinned host frames -> er_tsdf_integrate_batch
-              (host->device copies inside the timed region) + a device->host read of the step's result
-  roofline    integrate kernel: algorithmic bytes (16 B x updated voxels + 2 B x W x H per frame)
-              / its event-bracketed device time, against the measured HBM peak
+  value         frames/s with the frames already resident in HBM (er_tsdf_integrate_device)
+  e2e           frames/s through the C ABI with HOST buffers: pinned host frames -> device (inside the timed region),
+                integration, and the step's result -- the SaveWorld voxel list (er_tsdf_extract) -- back in pinned
+                host memory
+  roofline      integrate kernel (the production instantiation): algorithmic bytes (16 B x updated voxels + 2 B x W x H
+                per frame) / its event-bracketed device time, against the measured HBM peak; the updated
+                voxels are counted by a separate pass with the statistics build of the kernels
   cpu_baseline  the verbatim reference binary (oracle/_ref/Integrate_ref, its 8 OpenMP threads) on a bounded
-              prefix of the same frames, timed per frame on this box's host cores
-  icp         secondary metric of BASELINE.json: fragment-pair ICP iterations/s (same JSON line)
+                prefix of the same frames, timed per frame on this box's host cores
+  ctrlgrid      BASELINE configs[3]: the ControlGrid (nonrigid re-projection) mode on a 6 m room, pool of 4096 blocks
+  icp           second half of the metric: fragment-pair ICP iterations/s (icp_bench.py); `--metric icp` prints it as
+                the line itself, and `--impl reference --metric icp` times the CPU port of that path
 
-N > 1 (torchrun, one rank per GPU): every rank integrates its own frame stream into its own volume -- the
-path shards by independent volumes/fragments with no data-path collective -- so scaling is "weak" and
-value = total frames of all ranks / max-over-ranks time.
+N > 1 (torchrun, one rank per GPU): ONE volume, its 64^3 blocks partitioned over the ranks ((xi+yi+zi) % N == rank,
+er_tsdf_set_partition); every rank sees every frame, no data-path collective during integration ("scaling":
+"strong": the sequence is fixed, value = its frames / max-over-ranks time).  The e2e feed is sharded: rank r copies
+1/N of each chunk of frames over its own PCIe link and the ranks all-gather the chunk over NVLink (NCCL).  After the
+timed regions the union of the partitions is checked against an unpartitioned volume (order-independent digest of the
+extracted voxels).  The independent-replica number of round 1 (every rank its own volume and frame stream, weak
+scaling) is kept as `replica`.
 """
 from __future__ import annotations
 
@@ -41,6 +49,9 @@ from elasticreconstruction_b200 import synth  # noqa: E402
 SEQ_FRAMES = 1000            # configs[1]
 W, H = 640, 480
 BYTES_PER_FRAME = W * H * 2
+TSDF_METRIC = "depth frames/sec into 512^3 TSDF"
+ICP_METRIC = "fragment-pair ICP iterations/sec"
+WORKLOAD = "TSDF integrate: 1000 synthetic 640x480 frames, rigid trajectory, 512^3 @ 3/512 m (BASELINE configs[1])"
 
 
 # --------------------------------------------------------------------------------------------- helpers
@@ -111,13 +122,58 @@ class ClockSampler:
                 "samples": len(self.sm)}
 
 
-def make_sequence(rank: int, world: int):
-    """The configs[1] trajectory (camera->world) and a generator for its depth frames.  Rank r of a
-    multi-GPU run starts r/world of the way round the loop (its own independent stream)."""
+def make_sequence(rank: int = 0, world: int = 1):
+    """The configs[1] trajectory (camera->world).  Rank r of a replica run starts r/world of the way round the loop."""
     poses = synth.quantize_log(synth.loop_trajectory(SEQ_FRAMES))
     off = (rank * SEQ_FRAMES) // max(world, 1)
     order = (np.arange(SEQ_FRAMES) + off) % SEQ_FRAMES
     return poses[order]
+
+
+def room_depth_device(poses, device, lo=0.25, hi=2.75):
+    """synth.room_depth evaluated with torch on the GPU (same float64 formula; input generation is not timed)."""
+    import torch
+    T = torch.as_tensor(np.asarray(poses, dtype=np.float64).reshape(-1, 4, 4), device=device)
+    u = (torch.arange(W, dtype=torch.float64, device=device) - synth.CX) / synth.FX
+    v = (torch.arange(H, dtype=torch.float64, device=device) - synth.CY) / synth.FY
+    dirs = torch.stack([u[None, :].expand(H, W), v[:, None].expand(H, W), torch.ones((H, W), dtype=torch.float64, device=device)], -1)
+    out = torch.empty((len(T), H, W), dtype=torch.int16, device=device)
+    for i in range(len(T)):
+        d = dirs @ T[i, :3, :3].T
+        o = T[i, :3, 3]
+        t = torch.where(d > 0, (hi - o) / d, (lo - o) / d)
+        t = torch.where(d == 0, torch.full_like(t, float("inf")), t)
+        mm = torch.round(t.min(dim=-1).values * 1000.0)          # round half to even, like np.rint
+        mm = torch.where((mm > 0) & (mm < 65535), mm, torch.zeros_like(mm))
+        out[i] = mm.to(torch.int32).to(torch.int16)               # u16 bit pattern
+    return out
+
+
+def voxel_digest(xyzi: np.ndarray):
+    """Order-independent digest of an extracted voxel list [n,4] float32: (count, sum of 64-bit row hashes mod 2^64 as
+    two 32-bit halves).  Equal multisets give equal digests whatever the order or the partition."""
+    if len(xyzi) == 0:
+        return np.array([0, 0, 0], dtype=np.int64)
+    r = np.ascontiguousarray(xyzi, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        h = r[:, 0] * np.uint64(0x9E3779B97F4A7C15)
+        h ^= (r[:, 1] + np.uint64(0x7F4A7C15)) * np.uint64(0xC2B2AE3D27D4EB4F)
+        h ^= (r[:, 2] + np.uint64(0x165667B1)) * np.uint64(0xD6E8FEB86659FD93)
+        h ^= (r[:, 3] + np.uint64(0x27D4EB4F)) * np.uint64(0xA0761D6478BD642F)
+        h ^= h >> np.uint64(29)
+        h *= np.uint64(0xBF58476D1CE4E5B9)
+        h ^= h >> np.uint64(32)
+        s = np.uint64(h.sum(dtype=np.uint64))
+    return np.array([len(xyzi), int(s & np.uint64(0xFFFFFFFF)), int(s >> np.uint64(32))], dtype=np.int64)
+
+
+def digest_equal(total, single):
+    """`total` = element-wise sum over ranks of voxel_digest() triples; compare with one triple modulo 2^64."""
+    if int(total[0]) != int(single[0]):
+        return False
+    a = (int(total[1]) + (int(total[2]) << 32)) % (1 << 64)
+    b = (int(single[1]) + (int(single[2]) << 32)) % (1 << 64)
+    return a == b
 
 
 def dist_env():
@@ -134,6 +190,9 @@ def run_reference(args):
     rank, world, _ = dist_env()
     if rank != 0:
         return 0
+    if args.metric == "icp":
+        import icp_bench
+        return icp_bench.run_reference(args)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
     fps_step = args.ref_frames_per_step
@@ -169,11 +228,11 @@ def run_reference(args):
     sample = "%d steps x %d frames (prefix of the 1000-frame sequence), per-frame wall time of Execute()" % (
         args.steps, fps_step)
     line = {
-        "impl": "reference", "metric": "depth frames/sec into 512^3 TSDF", "value": value, "unit": "frames/s",
+        "impl": "reference", "metric": TSDF_METRIC, "value": value, "unit": "frames/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "TSDF integrate: 1000 synthetic 640x480 frames, rigid trajectory, 512^3 @ 3/512 m (BASELINE configs[1])",
-                   "frames_per_step": fps_step, "threads": 8, "host_cores": os.cpu_count()},
+        "higher_is_better": True, "scaling": "strong" if args.gpus > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": WORKLOAD, "frames_per_step": fps_step, "threads": 8, "host_cores": os.cpu_count()},
         "cpu_baseline": {"value": value, "unit": "frames/s", "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -214,6 +273,84 @@ def cpu_baseline_leg(poses, n_frames: int):
                       "Execute(); host has %d cores, reference hard-codes 8 threads" % (n_frames, skip, os.cpu_count())}
 
 
+# --------------------------------------------------------------------------------------------- ControlGrid leg
+def ctrlgrid_scene(n_frames: int, interval: int = 50, res: int = 8, length: float = 3.0):
+    """BASELINE configs[3] inputs: a loop through a 6 m room (16^3 blocks of 64^3 voxels = "~1024^3 hashed"),
+    fragments of `interval` frames, one control lattice per fragment = the fragment's pose applied to the regular
+    lattice (Pose2Ctr form, FragmentOptimizer/OptApp.cpp:735-750) plus a smooth displacement <= 1 cm; seg_traj = the
+    frame's pose relative to its fragment's volume (base pose t = (1.5, 1.5, -0.3), CorresApp.cpp:46-49)."""
+    num = n_frames // interval
+    world = synth.quantize_log(synth.loop_trajectory(n_frames, center=(3.0, 3.0, 3.0), radius=1.6, bob=0.4))
+    base = synth.BASEPOSE
+    base_inv = np.linalg.inv(base)
+    pose, seg = [], []
+    for c in range(num):
+        pose.append(world[c * interval] @ base_inv)
+        first_inv = np.linalg.inv(world[c * interval])
+        for j in range(interval):
+            seg.append(base @ first_inv @ world[c * interval + j])
+    seg.append(seg[-1])
+    pose = synth.quantize_log(np.array(pose))
+    seg = synth.quantize_log(np.array(seg))
+    frames0 = [np.linalg.inv(pose[0]) @ pose[c] for c in range(num)]
+    grids = synth.quantize_ctr(synth.make_control_grids(num, res, length, amp=0.01, frames=frames0))
+    return dict(world=world, pose=pose, seg=seg, grids=grids, num=num, interval=interval, res=res, length=length)
+
+
+def ctrlgrid_leg(args, local, rank, world, barrier, capi, torch, dist):
+    """Frames resident in HBM -> er_tsdf_reproject-on-device + ScaleDepth + Integrate per batch
+    (IntegrateApp.cpp:217-225 per frame), device-timed; reproject_kernel timed on its own."""
+    n = args.ctr_frames
+    sc = ctrlgrid_scene(n)
+    # traj[i*I+j] = pose[i] * seg[i*I+j] with the library's Eigen-order product (IntegrateApp.cpp:73)
+    traj = np.array([capi.mat4_mul(sc["pose"][f // sc["interval"]], sc["seg"][f]) for f in range(n)])
+    d_frames = room_depth_device(traj, torch.device("cuda", local), lo=0.25, hi=5.75)
+    chunks = (np.arange(n) // sc["interval"]).astype(np.int32)
+    vol = capi.TSDFVolume(device=local, max_blocks=args.ctr_pool)
+    vol.set_fusion(args.fusion)
+    vol.set_control_grids(sc["grids"], sc["res"], sc["length"])
+    if world > 1:
+        vol.set_partition(rank, world)
+    T0, A0 = traj[0], sc["seg"][0]
+
+    def run():
+        vol.integrate_ctr_device(d_frames.data_ptr(), traj, T0, A0, sc["seg"][:n], chunks)
+
+    for _ in range(3):
+        run()
+    vol.sync()
+    barrier()
+    l0 = vol.launch_count()
+    vol.event_record(0)
+    for _ in range(args.ctr_steps):
+        run()
+    vol.event_record(1)
+    vol.sync()
+    barrier()
+    ms = vol.event_elapsed_ms(0, 1)
+    launches = vol.launch_count() - l0
+    rp_ms = vol.profile_reproject_device(d_frames.data_ptr(), traj, T0, A0, sc["seg"][:n], chunks)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    nb = vol.num_blocks()
+    nbt = torch.tensor([float(nb)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(nbt, op=dist.ReduceOp.SUM)
+    out = {"metric": "depth frames/sec, ControlGrid mode (BASELINE configs[3])",
+           "value": n * args.ctr_steps / (float(t.item()) * 1e-3), "unit": "frames/s",
+           "config": {"workload": "TSDF integrate with ControlGrid nonrigid re-projection: %d synthetic 640x480 frames of a loop "
+                                  "through a 6 m room, %d fragments x %d frames, lattice res %d, block pool %d per rank, blocks "
+                                  "partitioned over %d rank(s)" % (n, sc["num"], sc["interval"], sc["res"], args.ctr_pool, world),
+                      "frames": n, "passes_timed": args.ctr_steps},
+           "ms_per_pass": float(t.item()) / args.ctr_steps, "allocated_blocks": int(nbt.item()), "gpu_launches": int(launches),
+           "reproject_us_per_frame": 1e3 * rp_ms / n,
+           "reproject_note": "reproject_kernel + z-buffer reset/convert of one frame, event-bracketed on the stream; algorithmic "
+                             "bytes 2 B read + 4 B atomicMin + 4+2 B convert per pixel = 3.7 MB/frame"}
+    del vol
+    return out
+
+
 # --------------------------------------------------------------------------------------------- main arm
 def main():
     ap = argparse.ArgumentParser()
@@ -221,14 +358,23 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--metric", default="tsdf", choices=["tsdf", "icp"],
+                    help="which half of BASELINE.json's metric the printed line carries (the TSDF line always embeds `icp`)")
     ap.add_argument("--frames-per-step", type=int, default=SEQ_FRAMES,
                     help="frames handed to the library per call; must divide the 1000-frame sequence")
     ap.add_argument("--ref-frames-per-step", type=int, default=8)
+    ap.add_argument("--ref-pairs-per-step", type=int, default=4)
     ap.add_argument("--cpu-frames", type=int, default=120, help="frames timed for cpu_baseline (0 = skip)")
     ap.add_argument("--fusion", type=int, default=32, help="frames per fused launch triple (1..32)")
     ap.add_argument("--no-icp", action="store_true")
+    ap.add_argument("--no-ctr", action="store_true")
+    ap.add_argument("--no-replica", action="store_true")
     ap.add_argument("--icp-fragments", type=int, default=50)
     ap.add_argument("--icp-points", type=int, default=200000)
+    ap.add_argument("--ctr-frames", type=int, default=1000)
+    ap.add_argument("--ctr-steps", type=int, default=3)
+    ap.add_argument("--ctr-pool", type=int, default=4096)
+    ap.add_argument("--e2e-chunk", type=int, default=125, help="frames per H2D/all-gather chunk of the sharded feed (N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -246,68 +392,106 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def rmax(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    peak, peak_src = load_peaks()
+    if args.metric == "icp":
+        import icp_bench
+        icp = icp_bench.run(local, rank, world, barrier, peak_gbs=peak, num_fragments=args.icp_fragments,
+                            points=args.icp_points, clock_sampler=ClockSampler)
+        if rank == 0:
+            line = icp_bench.as_line(icp, args, world)
+            sys.stdout.flush()
+            os.write(real_stdout, (json.dumps(line) + "\n").encode())
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
     F = args.frames_per_step
     nsteps = args.warmup + args.steps
-    poses = make_sequence(rank, world)
-    # every step's frames, generated once on the host (synthetic, analytic room)
     need = min(SEQ_FRAMES, F * nsteps)
-    frames_np = synth.room_depth(poses[:need])
-    step_idx = [(np.arange(F) + s * F) % need for s in range(nsteps)]
-
-    # ---------------- value: frames resident in HBM
-    d_frames = torch.from_numpy(frames_np.view(np.int16)).cuda(local)
-    vol = capi.TSDFVolume(device=local, max_blocks=1024)
-    vol.set_fusion(args.fusion)
-    torch.cuda.synchronize()
-
     assert need % F == 0, "--frames-per-step must divide the resident sequence so every step is one contiguous run"
+    step_idx = [(np.arange(F) + s * F) % need for s in range(nsteps)]
+    partitioned = world > 1
 
-    def run_step_device(s):
-        idx = step_idx[s]
-        vol.integrate_device(d_frames.data_ptr() + int(idx[0]) * BYTES_PER_FRAME, poses[idx], F)
+    def new_volume(part: bool, pool: int = 1024):
+        v = capi.TSDFVolume(device=local, max_blocks=pool)
+        v.set_fusion(args.fusion)
+        if part:
+            v.set_partition(rank, world)
+        return v
 
-    for s in range(args.warmup):
-        run_step_device(s)
-    vol.sync()
-    sampler = ClockSampler(local)
-    barrier()
-    sampler.start()
-    l0 = vol.launch_count()
-    vol.event_record(0)
-    t0 = time.perf_counter()
-    for s in range(args.warmup, nsteps):
-        run_step_device(s)
-    vol.event_record(1)
-    vol.sync()
-    barrier()
-    wall = time.perf_counter() - t0
-    clocks = sampler.stop()
-    dev_ms = vol.event_elapsed_ms(0, 1)
-    launches = vol.launch_count() - l0
-    t = torch.tensor([dev_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max = float(t.item())
-    total_frames = F * args.steps * world
-    value = total_frames / (dev_ms_max * 1e-3)
+    def timed_device_run(vol, d_frames, poses):
+        """W warm-up + K timed steps with the frames resident; returns (max-over-ranks device ms, launches, clocks, wall)."""
+        def step(s):
+            idx = step_idx[s]
+            vol.integrate_device(d_frames.data_ptr() + int(idx[0]) * BYTES_PER_FRAME, poses[idx], F)
+        for s in range(args.warmup):
+            step(s)
+        vol.sync()
+        sampler = ClockSampler(local)
+        barrier()
+        sampler.start()
+        l0 = vol.launch_count()
+        vol.event_record(0)
+        t0 = time.perf_counter()
+        for s in range(args.warmup, nsteps):
+            step(s)
+        vol.event_record(1)
+        vol.sync()
+        barrier()
+        wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+        return rmax(vol.event_elapsed_ms(0, 1)), vol.launch_count() - l0, clocks, wall
 
-    # ---------------- roofline: per-kernel time + exact updated-voxel count on the timed frames
-    vol2 = capi.TSDFVolume(device=local, max_blocks=1024)
-    vol2.set_fusion(args.fusion)
+    # ---------------- value: the configs[1] sequence, frames resident in HBM; N > 1: one volume, blocks partitioned
+    poses = make_sequence(0, 1)
+    d_frames = room_depth_device(poses[:need], dev)
+    vol = new_volume(partitioned)
+    dev_ms, launches, clocks, wall = timed_device_run(vol, d_frames, poses)
+    total_frames = F * args.steps
+    value = total_frames / (dev_ms * 1e-3)
+    owned_blocks = vol.num_blocks()
+    del vol
+
+    # ---------------- union check (N > 1, untimed): the partitions together hold exactly the unpartitioned volume
+    union = None
+    if partitioned:
+        vp = new_volume(True)
+        vp.integrate_device(d_frames.data_ptr(), poses[:need], need)
+        dg = torch.from_numpy(voxel_digest(vp.extract())).cuda()
+        del vp
+        dist.all_reduce(dg, op=dist.ReduceOp.SUM)
+        ok = None
+        if rank == 0:
+            vs = new_volume(False)
+            vs.integrate_device(d_frames.data_ptr(), poses[:need], need)
+            single = voxel_digest(vs.extract())
+            del vs
+            ok = bool(digest_equal(dg.cpu().numpy(), single))
+        union = {"voxels": int(dg[0].item()), "equal_to_unpartitioned_volume": ok,
+                 "how": "order-independent 64-bit digest of (x, y, z, tsdf) rows of er_tsdf_extract after one pass over the "
+                        "sequence: sum over ranks vs one unpartitioned volume on rank 0"}
+
+    # ---------------- roofline: production kernels timed one by one (overlap off), updated voxels counted separately
+    vol2 = new_volume(partitioned)
     for s in range(args.warmup):
         idx = step_idx[s]
         vol2.integrate_device(d_frames.data_ptr() + int(idx[0]) * BYTES_PER_FRAME, poses[idx], F)
-    vol2.set_stats(True)
     vol2.sync()
-    st0 = vol2.stats()
     t_touch = t_cls = t_int = 0.0
     for s in range(args.warmup, nsteps):
         idx = step_idx[s]
@@ -315,61 +499,137 @@ def main():
         t_touch += a
         t_cls += b
         t_int += c
+    del vol2
+    # the statistics build of the kernels on one pass over the sequence in steady state (every pass updates the same voxels)
+    vol2 = new_volume(partitioned)
+    vol2.integrate_device(d_frames.data_ptr(), poses[:need], need)
+    vol2.set_stats(True)
+    vol2.sync()
+    st0 = vol2.stats()
+    vol2.integrate_device(d_frames.data_ptr(), poses[:need], need)
     st1 = vol2.stats()
+    del vol2
     n_prof = F * args.steps
     fusion = args.fusion
     n_launch = args.steps * ((F + fusion - 1) // fusion)          # integrate_kernel launches in the profiled pass
-    upd = st1["updated_voxels"] - st0["updated_voxels"]
-    blocks = st1["touched_blocks"] - st0["touched_blocks"]
-    alg_bytes_per_launch = (16.0 * upd + 2.0 * W * H * n_prof) / n_launch
+    upd_pf = (st1["updated_voxels"] - st0["updated_voxels"]) / need           # per frame, this rank's blocks
+    blocks_pf = (st1["touched_blocks"] - st0["touched_blocks"]) / need
+    alg_bytes_per_launch = (16.0 * upd_pf + 2.0 * W * H) * n_prof / n_launch
     int_s_per_launch = t_int * 1e-3 / n_launch
-    peak, peak_src = load_peaks()
     achieved = alg_bytes_per_launch / int_s_per_launch / 1e9
-    roofline = {"bound": "hbm", "kernel": "integrate_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "peak_source": peak_src, "traffic": load_traffic("integrate_kernel"),
+    full_pairs = (st1["full_pairs"] - st0["full_pairs"]) / need
+    one_pairs = (st1["one_pairs"] - st0["one_pairs"]) / need
+    roofline = {"bound": "hbm", "kernel": "integrate_kernel<false,4> (production instantiation)", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src, "traffic": load_traffic("integrate_kernel"),
                 "traffic_source": "ncu --set full capture of one 32-frame launch (profiles/traffic.json)",
                 "algorithmic_bytes_per_launch": alg_bytes_per_launch, "us_per_launch": int_s_per_launch * 1e6,
                 "frames_per_launch": n_prof / n_launch,
-                "note": "algorithmic bytes = 16 B x updated voxels + 2 B x W x H per frame (SURVEY 8d); one launch "
-                        "applies a whole batch of frames to register-resident voxels, so achieved may exceed DRAM traffic",
+                "note": "algorithmic bytes = 16 B x updated voxels + 2 B x W x H per frame (SURVEY 8d); one launch applies a whole "
+                        "batch of frames to register-resident voxels and consecutive batches find their blocks in L2, so DRAM "
+                        "traffic is far below the algorithmic bytes: the kernel is instruction-issue bound (see `issue`), the "
+                        "HBM fraction is reported because the metric asks for it",
+                "issue": load_issue_stats(),
                 "touch_us_per_frame": t_touch * 1e3 / n_prof, "classify_us_per_frame": t_cls * 1e3 / n_prof,
-                "integrate_us_per_frame": t_int * 1e3 / n_prof,
-                "updated_voxels_per_frame": upd / n_prof, "active_blocks_per_frame": blocks / n_prof,
-                "one_voxels_per_frame": 64.0 * (st1["one_pairs"] - st0["one_pairs"]) / n_prof,
-                "full_voxels_per_frame": 64.0 * (st1["full_pairs"] - st0["full_pairs"]) / n_prof,
-                "dense_bytes_per_frame": 16.0 * 262144 * blocks / n_prof + 2.0 * W * H}
-    del vol2
+                "integrate_us_per_frame": t_int * 1e3 / n_prof, "serial_us_per_frame": (t_touch + t_cls + t_int) * 1e3 / n_prof,
+                "pipelined_us_per_frame": dev_ms * 1e3 / total_frames,
+                "updated_voxels_per_frame": upd_pf, "active_blocks_per_frame": blocks_pf,
+                "one_voxels_per_frame": 64.0 * one_pairs, "full_voxels_per_frame": 64.0 * full_pairs,
+                "dense_bytes_per_frame": 16.0 * 262144 * blocks_pf + 2.0 * W * H}
 
-    # ---------------- e2e: host buffers through the C ABI, H2D inside the timed region
-    pinned = torch.from_numpy(frames_np.view(np.int16)).pin_memory()
-    vol3 = capi.TSDFVolume(device=local, max_blocks=1024)
-    vol3.set_fusion(args.fusion)
+    # ---------------- e2e: host buffers through the C ABI, H2D inside the timed region, the voxel list back on the host
+    frames_host = d_frames.cpu()
+    pinned = frames_host.pin_memory()
+    del frames_host
+    vol3 = new_volume(partitioned)
+    cap_rows = 0
+    result = None
+
+    if partitioned:
+        # sharded feed: rank r copies its 1/N slice of every chunk over its own PCIe link, the ranks all-gather the chunk
+        # over NVLink (NCCL), the library integrates it from HBM; two chunk buffers so that the copy/gather of chunk c + 1
+        # runs while chunk c is integrated
+        C = args.e2e_chunk
+        assert F % C == 0 and C % world == 0, "--e2e-chunk must divide --frames-per-step and be a multiple of the rank count"
+        per = C // world
+        gath = [torch.empty((C, H, W), dtype=torch.int16, device=dev) for _ in range(2)]
+        mine = [torch.empty((per, H, W), dtype=torch.int16, device=dev) for _ in range(2)]
+        feed_stream = torch.cuda.Stream(device=dev)
+
+        def e2e_step(s):
+            f0 = int(step_idx[s][0])
+            nchunk = F // C
+            evs = [None, None]
+
+            def issue(c):                       # copy + gather chunk c into buffer c & 1 (asynchronous, feed stream)
+                b = c & 1
+                with torch.cuda.stream(feed_stream):
+                    lo = f0 + c * C + rank * per
+                    mine[b].copy_(pinned[lo:lo + per], non_blocking=True)
+                    dist.all_gather_into_tensor(gath[b], mine[b])
+                    evs[b] = torch.cuda.Event()
+                    evs[b].record(feed_stream)
+
+            issue(0)
+            for c in range(nchunk):
+                if c + 1 < nchunk:
+                    if c >= 1:
+                        vol3.inputs_consumed()  # chunk c - 1 has been read: its buffer may be overwritten by chunk c + 1
+                    issue(c + 1)
+                evs[c & 1].synchronize()
+                vol3.integrate_device(gath[c & 1].data_ptr(), poses[f0 + c * C: f0 + (c + 1) * C], C)
+            vol3.inputs_consumed()
+        h2d_per_step = F * BYTES_PER_FRAME // world
+        feed = "sharded: 1/N of each %d-frame chunk per rank over PCIe, NCCL all-gather over NVLink, er_tsdf_integrate_device" % C
+    else:
+        def e2e_step(s):
+            idx = step_idx[s]
+            vol3.integrate_ptr(pinned.data_ptr() + int(idx[0]) * BYTES_PER_FRAME, poses[idx], F)
+        h2d_per_step = F * BYTES_PER_FRAME
+        feed = "er_tsdf_integrate_batch from pinned host memory"
+
     for s in range(args.warmup):
-        idx = step_idx[s]
-        vol3.integrate_ptr(pinned.data_ptr() + int(idx[0]) * BYTES_PER_FRAME, poses[idx], F)
-        vol3.num_blocks()
+        e2e_step(s)
+    cap_rows = int(vol3.extract_count() * 1.05) + 1024
+    result = capi.HostBuffer(cap_rows * 16)
+    n_rows = vol3.extract_into(result, cap_rows)
     barrier()
     t0 = time.perf_counter()
     for s in range(args.warmup, nsteps):
-        idx = step_idx[s]
-        vol3.integrate_ptr(pinned.data_ptr() + int(idx[0]) * BYTES_PER_FRAME, poses[idx], F)
-        vol3.num_blocks()            # device->host read of the step's result (forces completion)
+        e2e_step(s)
+        n_rows = vol3.extract_into(result, cap_rows)      # SaveWorld's voxel list of the step, device -> pinned host
     barrier()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e = {"value": total_frames / float(t.item()), "unit": "frames/s", "h2d_bytes_per_step": F * BYTES_PER_FRAME,
-           "d2h_bytes_per_step": 4 + 32, "timing": "wall clock around the C-ABI calls, barrier+sync both sides"}
-    del vol3
+    e2e_s = rmax(time.perf_counter() - t0)
+    e2e = {"value": total_frames / e2e_s, "unit": "frames/s", "h2d_bytes_per_step": int(h2d_per_step),
+           "d2h_bytes_per_step": int(n_rows * 16 + 8), "result_rows": int(n_rows), "feed": feed,
+           "timing": "wall clock around the C-ABI calls (integrate + er_tsdf_extract of the step's voxels into pinned host "
+                     "memory), barrier+sync both sides, max over ranks"}
+    del vol3, result
 
-    # ---------------- ICP secondary metric, then the cpu baseline (rank 0, N = 1 only; last, so that no GPU leg starts
-    # from the idle clocks the GPU drops to while the host is busy)
+    # ---------------- replica mode of round 1 (N > 1): every rank its own volume and its own frame stream
+    replica = None
+    if partitioned and not args.no_replica:
+        rposes = make_sequence(rank, world)
+        rframes = room_depth_device(rposes[:need], dev)
+        rv = new_volume(False)
+        rms, _, _, _ = timed_device_run(rv, rframes, rposes)
+        replica = {"value": total_frames * world / (rms * 1e-3), "unit": "frames/s", "scaling": "weak",
+                   "sharding": "independent volume and frame stream per rank (round 1's mode)"}
+        del rv, rframes
+
+    del d_frames, pinned
+    torch.cuda.empty_cache()
+
+    # ---------------- configs[3]: ControlGrid mode
+    ctr = None
+    if not args.no_ctr:
+        ctr = ctrlgrid_leg(args, local, rank, world, barrier, capi, torch, dist)
+        torch.cuda.empty_cache()
+
+    # ---------------- ICP (second half of the metric), then the cpu baseline (rank 0, N = 1 only; last, so that no GPU leg
+    # starts from the idle clocks the GPU drops to while the host is busy)
     icp = None
     if not args.no_icp:
-        del vol, d_frames, pinned
-        torch.cuda.empty_cache()
-        from elasticreconstruction_b200 import icp_bench
+        import icp_bench
         icp = icp_bench.run(local, rank, world, barrier, peak_gbs=peak, num_fragments=args.icp_fragments,
                             points=args.icp_points, clock_sampler=ClockSampler)
     cpu = None
@@ -378,22 +638,34 @@ def main():
 
     if rank == 0:
         line = {
-            "metric": "depth frames/sec into 512^3 TSDF", "value": value, "unit": "frames/s", "n_gpus": world,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms_max / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "TSDF integrate: 1000 synthetic 640x480 frames, rigid trajectory, 512^3 @ 3/512 m "
-                                   "(BASELINE configs[1])",
-                       "frames_per_step": F, "frames_per_launch": args.fusion, "block_pool": 1024, "sharding": "independent volume per rank" if world > 1 else "single volume",
+            "metric": TSDF_METRIC, "value": value, "unit": "frames/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps,
+            "higher_is_better": True, "scaling": "strong" if partitioned else "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "frames_per_step": F, "frames_per_launch": args.fusion, "block_pool": 1024,
+                       "sharding": ("blocks partitioned: one volume, rank r owns the 64^3 blocks with (xi+yi+zi) %% %d == r; every "
+                                    "rank sees every frame; no data-path collective" % world) if partitioned else "single volume",
                        "l2": "inputs larger than L2 (resident depth sequence %.0f MB + 2 GiB block pool); consecutive "
                              "frames legitimately reuse their active blocks through L2" % (need * BYTES_PER_FRAME / 1e6)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-            "wall_s_timed_region": wall, "icp": icp,
+            "wall_s_timed_region": wall, "blocks_owned_rank0": owned_blocks, "union_check": union, "replica": replica,
+            "ctrlgrid": ctr, "icp": icp,
         }
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def load_issue_stats():
+    """Instruction-issue figures of the integrate kernel from the committed ncu capture (profiles/traffic.json): the roof
+    that actually binds it."""
+    p = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        return json.load(open(p))["integrate_kernel"].get("issue")
+    except Exception:
+        return None
 
 
 if __name__ == "__main__":

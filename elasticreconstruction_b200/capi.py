@@ -32,6 +32,8 @@ SIGNATURES = {
     "er_build_arch": (C.c_char_p, []),
     "er_mat4_mul": (None, [c_dp, c_dp, c_dp]),
     "er_mat4_inverse": (None, [c_dp, c_dp]),
+    "er_host_alloc": (C.c_void_p, [C.c_size_t]),
+    "er_host_free": (None, [C.c_void_p]),
     "er_tsdf_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_double, C.c_size_t]),
     "er_tsdf_destroy": (None, [C.c_void_p]),
     "er_tsdf_set_stream": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -45,6 +47,9 @@ SIGNATURES = {
     "er_tsdf_integrate": (C.c_int, [C.c_void_p, c_u16p, c_dp]),
     "er_tsdf_integrate_ctr": (C.c_int, [C.c_void_p, c_u16p, c_dp, c_dp, c_dp, c_dp, C.c_int]),
     "er_tsdf_integrate_ctr_batch": (C.c_int, [C.c_void_p, c_u16p, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int]),
+    "er_tsdf_integrate_ctr_device": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int]),
+    "er_tsdf_profile_reproject_device": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, c_dp, c_dp, c_dp, c_ip, C.c_int, c_fp]),
+    "er_tsdf_inputs_consumed": (C.c_int, [C.c_void_p]),
     "er_tsdf_integrate_batch": (C.c_int, [C.c_void_p, c_u16p, c_dp, C.c_int]),
     "er_tsdf_integrate_device": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, C.c_int]),
     "er_tsdf_profile_device": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, C.c_int, c_fp, c_fp, c_fp]),
@@ -61,6 +66,10 @@ SIGNATURES = {
     "er_cloud_free": (None, [C.c_void_p]),
     "er_cloud_size": (C.c_size_t, [C.c_void_p]),
     "er_icp_count_inliers": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, C.c_double, c_ip]),
+    "er_icp_count_inliers_batch": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, c_ip, c_ip, C.c_int, c_dp, C.c_double, c_ip]),
+    "er_icp_correspondences_batch": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, c_ip, c_ip, C.c_int, c_dp, C.c_double,
+                                               C.c_double, c_i32p, C.c_size_t, c_szp, c_dp]),
+    "er_icp_release": (C.c_int, [C.c_int]),
     "er_icp_align": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, C.c_double, C.c_int, C.c_double, C.c_int, c_dp, c_ip, c_dp]),
     "er_icp_align_batch": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, c_ip, c_ip, C.c_int, c_dp, C.c_double, C.c_int,
                                      C.c_double, C.c_int, c_dp, c_ip, c_dp]),
@@ -124,6 +133,32 @@ def mat4_inverse(m) -> np.ndarray:
     out = np.empty(16, dtype=np.float64)
     lib().er_mat4_inverse(_dp(_mat(m)), _dp(out))
     return out.reshape(4, 4)
+
+
+class HostBuffer:
+    """Page-locked host memory from er_host_alloc (frame buffers / result buffers of the *_batch and extract calls)."""
+
+    def __init__(self, nbytes: int):
+        self.nbytes = int(nbytes)
+        self.ptr = lib().er_host_alloc(self.nbytes)
+        if not self.ptr:
+            raise ElasticError("er_host_alloc failed: " + lib().er_last_error().decode("utf-8", "replace"))
+
+    def array(self, dtype, count=None):
+        dt = np.dtype(dtype)
+        n = self.nbytes // dt.itemsize if count is None else count
+        return np.ctypeslib.as_array(C.cast(C.c_void_p(self.ptr), C.POINTER(C.c_uint8)), shape=(self.nbytes,)).view(dt)[:n]
+
+    def close(self):
+        if getattr(self, "ptr", None):
+            lib().er_host_free(C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class TSDFVolume:
@@ -244,6 +279,30 @@ class TSDFVolume:
         _check(lib().er_tsdf_integrate_ctr_batch(self._h, _u16p(d), _dp(Ti), _dp(_mat(T0)), _dp(_mat(A0)), _dp(Ai),
                                                  ch.ctypes.data_as(c_ip), n))
 
+    def _ctr_args(self, Ti, T0, A0, Ai, chunks):
+        Ti = np.ascontiguousarray(Ti, dtype=np.float64).reshape(-1, 16)
+        Ai = np.ascontiguousarray(Ai, dtype=np.float64).reshape(-1, 16)
+        ch = np.ascontiguousarray(chunks, dtype=np.int32)
+        assert Ti.shape[0] >= len(ch) and Ai.shape[0] >= len(ch)
+        return Ti, _mat(T0), _mat(A0), Ai, ch
+
+    def integrate_ctr_device(self, device_ptr: int, Ti, T0, A0, Ai, chunks):
+        """ControlGrid mode with the frames resident in HBM."""
+        Ti, T0, A0, Ai, ch = self._ctr_args(Ti, T0, A0, Ai, chunks)
+        _check(lib().er_tsdf_integrate_ctr_device(self._h, C.c_void_p(device_ptr), _dp(Ti), _dp(T0), _dp(A0), _dp(Ai),
+                                                  ch.ctypes.data_as(c_ip), len(ch)))
+
+    def profile_reproject_device(self, device_ptr: int, Ti, T0, A0, Ai, chunks) -> float:
+        """Device milliseconds of the re-projection alone over the resident frames."""
+        Ti, T0, A0, Ai, ch = self._ctr_args(Ti, T0, A0, Ai, chunks)
+        ms = C.c_float()
+        _check(lib().er_tsdf_profile_reproject_device(self._h, C.c_void_p(device_ptr), _dp(Ti), _dp(T0), _dp(A0), _dp(Ai),
+                                                      ch.ctypes.data_as(c_ip), len(ch), C.byref(ms)))
+        return ms.value
+
+    def inputs_consumed(self):
+        _check(lib().er_tsdf_inputs_consumed(self._h))
+
     def sync(self):
         _check(lib().er_tsdf_sync(self._h))
 
@@ -276,6 +335,18 @@ class TSDFVolume:
             _check(lib().er_tsdf_extract(self._h, _fp(out), n.value, C.byref(m)))
             assert m.value == n.value
         return out
+
+    def extract_count(self) -> int:
+        n = C.c_size_t()
+        _check(lib().er_tsdf_extract(self._h, None, 0, C.byref(n)))
+        return n.value
+
+    def extract_into(self, hostbuf: "HostBuffer", cap_rows: int) -> int:
+        """SaveWorld's voxel list into a (pinned) host buffer of cap_rows x 16 bytes; returns the number of rows."""
+        assert hostbuf.nbytes >= cap_rows * 16
+        n = C.c_size_t()
+        _check(lib().er_tsdf_extract(self._h, C.cast(C.c_void_p(hostbuf.ptr), c_fp), cap_rows, C.byref(n)))
+        return n.value
 
     def save_world(self, path: str) -> int:
         """Write world.pcd exactly as pcl::io::savePCDFile(binary) does for PointXYZI (TSDFVolume.cpp:130)."""
@@ -375,6 +446,41 @@ def icp_correspondences(tgt: Cloud, src: Cloud, T, dist=0.015, normal_cos=0.8660
                                         pairs.ctypes.data_as(c_i32p), cap, C.byref(n),
                                         _dp(info) if want_info else None))
     return pairs[: n.value].copy(), (info.reshape(6, 6) if want_info else None)
+
+
+def icp_count_inliers_batch(clouds, tgt_idx, src_idx, T, dist: float) -> np.ndarray:
+    """The gate for a whole candidate list in one launch (pair loop of CorresApp.cpp:220-264)."""
+    n = len(tgt_idx)
+    arr = (C.c_void_p * len(clouds))(*[c._h for c in clouds])
+    ti = np.ascontiguousarray(tgt_idx, dtype=np.int32)
+    si = np.ascontiguousarray(src_idx, dtype=np.int32)
+    Ts = np.ascontiguousarray(T, dtype=np.float64).reshape(n, 16)
+    cnt = np.zeros(n, dtype=np.int32)
+    _check(lib().er_icp_count_inliers_batch(arr, len(clouds), ti.ctypes.data_as(c_ip), si.ctypes.data_as(c_ip), n, _dp(Ts),
+                                            float(dist), cnt.ctypes.data_as(c_ip)))
+    return cnt
+
+
+def icp_correspondences_batch(clouds, tgt_idx, src_idx, T, dist=0.015, normal_cos=0.8660, want_info=True):
+    """FindCorrespondence for a list of pairs (CorresApp.cpp:121-208): ([pairs_p [m_p,2]], info [n,6,6] or None)."""
+    n = len(tgt_idx)
+    arr = (C.c_void_p * len(clouds))(*[c._h for c in clouds])
+    ti = np.ascontiguousarray(tgt_idx, dtype=np.int32)
+    si = np.ascontiguousarray(src_idx, dtype=np.int32)
+    Ts = np.ascontiguousarray(T, dtype=np.float64).reshape(n, 16)
+    cap = int(sum(len(clouds[j]) for j in src_idx))
+    rows = np.empty((max(cap, 1), 2), dtype=np.int32)
+    start = np.zeros(n + 1, dtype=np.uintp)
+    info = np.zeros((n, 36), dtype=np.float64) if want_info else None
+    _check(lib().er_icp_correspondences_batch(arr, len(clouds), ti.ctypes.data_as(c_ip), si.ctypes.data_as(c_ip), n, _dp(Ts),
+                                              float(dist), float(normal_cos), rows.ctypes.data_as(c_i32p), cap,
+                                              start.ctypes.data_as(c_szp), _dp(info) if want_info else None))
+    out = [rows[int(start[p]):int(start[p + 1])].copy() for p in range(n)]
+    return out, (info.reshape(n, 6, 6) if want_info else None)
+
+
+def icp_release(device: int = 0):
+    _check(lib().er_icp_release(device))
 
 
 def icp_event_record(device: int, slot: int):

@@ -56,9 +56,25 @@ constexpr int kMaxItems = 32 * ((2 * kMaxRings + 1) * (2 * kMaxRings + 1) + 1);
 constexpr int kRunCap = 64;            // per-warp list of point runs waiting to be scanned (drained at 32)
 constexpr int kNoMatch = 0x7fffffff;
 
+// The working copy of a pair's source points is streamed (read once, written once per iteration, 2.4 MB each way per
+// pair): -DER_ICP_CUR_STREAM=1 marks those accesses evict-first so that they do not push the target grids, which
+// every query gathers from, out of L2.
+#ifndef ER_ICP_CUR_STREAM
+#define ER_ICP_CUR_STREAM 1
+#endif
+#if ER_ICP_CUR_STREAM
+#define ER_LDCUR(p) __ldcs(p)
+#define ER_STCUR(p, v) __stcs((p), (v))
+#else
+#define ER_LDCUR(p) (*(p))
+#define ER_STCUR(p, v) (*(p) = (v))
+#endif
+
 struct PairState {
   GridDev tgt;
   float* cur;             // source points, transformed in place iteration by iteration (n_src * 3)
+  const er_float4* src4;  // first iteration reads the fragment itself instead of a copy: cell-sorted points (x, y, z, index)
+  const float* src3;      // ... or, when src4 is null, the points in file order
   int n_src;
   int nblocks;
   double* partials;       // nblocks * kAcc
@@ -139,7 +155,7 @@ __device__ __forceinline__ void icp_rows(const PairState& S, const GridDev& g, c
     const float md2 = __uint_as_float((unsigned)(key >> 32));
     if (idx == kNoMatch || (double)md2 > max_d2) continue;
     const float* cp = S.cur + 3 * (size_t)(k0 + it * kThreads);
-    const float sx = cp[0], sy = cp[1], sz = cp[2];
+    const float sx = ER_LDCUR(cp), sy = ER_LDCUR(cp + 1), sz = ER_LDCUR(cp + 2);
     const float* tp = g.xyz_orig + 3 * (size_t)idx;
     const float* np = g.nrm_orig + 3 * (size_t)idx;
     const float dx = __ldg(tp), dy = __ldg(tp + 1), dz = __ldg(tp + 2), nx = __ldg(np), ny = __ldg(np + 1), nz = __ldg(np + 2);
@@ -178,7 +194,7 @@ __device__ __forceinline__ void icp_rows(const PairState& S, const GridDev& g, c
 
 template <bool COOP, int MINB>
 __global__ void __launch_bounds__(kThreads, MINB * 128 / kThreads) icp_iter_kernel(PairState* states, double max_d2, float bd_init, int max_iter,
-                                                            double eps, int fixed_iters) {
+                                                            double eps, int fixed_iters, int first) {
   PairState& S = states[blockIdx.y];
   if (blockIdx.x >= S.nblocks || S.done) return;
   __shared__ double s_part[kThreads / 32][kAcc];
@@ -203,12 +219,18 @@ __global__ void __launch_bounds__(kThreads, MINB * 128 / kThreads) icp_iter_kern
     float sx = 0.0f, sy = 0.0f, sz = 0.0f;
     if (k < S.n_src) {
       float* cp = S.cur + 3 * (size_t)k;
-      const float x = cp[0], y = cp[1], z = cp[2];
+      float x, y, z;
+      if (first) {                      // the working copy is created by the first iteration (no separate copy pass)
+        if (S.src4) { const er_float4 p = __ldg(&S.src4[k]); x = p.x; y = p.y; z = p.z; }
+        else { const float* sp = S.src3 + 3 * (size_t)k; x = __ldg(sp); y = __ldg(sp + 1); z = __ldg(sp + 2); }
+      } else {
+        x = ER_LDCUR(cp); y = ER_LDCUR(cp + 1); z = ER_LDCUR(cp + 2);
+      }
       // Matrix4f * (x, y, z, 1): ((m0*x + m1*y) + m2*z) + m3*1
       sx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[0], x), __fmul_rn(M[1], y)), __fmul_rn(M[2], z)), M[3]);
       sy = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[4], x), __fmul_rn(M[5], y)), __fmul_rn(M[6], z)), M[7]);
       sz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(M[8], x), __fmul_rn(M[9], y)), __fmul_rn(M[10], z)), M[11]);
-      cp[0] = sx; cp[1] = sy; cp[2] = sz;
+      ER_STCUR(cp, sx); ER_STCUR(cp + 1, sy); ER_STCUR(cp + 2, sz);
     }
     if (!COOP) {
       if (k < S.n_src) {
@@ -456,46 +478,73 @@ __device__ __forceinline__ void xform_normal(const XformD& X, const float* n, fl
   oz = (float)__dadd_rn(__dadd_rn(__dmul_rn(X.T[8], x), __dmul_rn(X.T[9], y)), __dmul_rn(X.T[10], z));
 }
 
+// ---- batched gate / correspondence passes: one job per pair, blockIdx.y = pair, so that a whole candidate list costs
+// one launch sequence and one synchronisation (the reference runs these pair-parallel from OpenMP threads,
+// CorresApp.cpp:121,220)
+struct GateJob {
+  GridDev tgt;
+  const float* src_xyz;
+  int n;
+  XformD X;
+};
+struct CorrJob {
+  GridDev tgt;
+  const float* src_xyz;
+  const float* src_nrm;
+  int n, nblk;
+  XformD X;
+  int* match;        // n
+  int* cta_count;    // nblk
+  int* offsets;      // nblk + 1
+  double* info;      // 13 sums or null
+};
+
 // gate of CCorresApp::Registration (CorresApp.cpp:257-264)
-__global__ void __launch_bounds__(kThreads) count_inliers_kernel(GridDev g, const float* __restrict__ src_xyz, int n,
-                                                                 XformD X, double d2max, int* count) {
+__global__ void __launch_bounds__(kThreads) count_inliers_kernel(const GateJob* __restrict__ jobs, double d2max,
+                                                                 int* __restrict__ counts) {
+  const GateJob& J = jobs[blockIdx.y];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((int)(blockIdx.x * blockDim.x) >= J.n) return;
   bool in = false;
-  if (k < n) {
+  if (k < J.n) {
     float qx, qy, qz, d2;
-    xform_point(X, src_xyz + 3 * (size_t)k, qx, qy, qz);
-    in = nn_search(g, qx, qy, qz, d2) >= 0 && (double)d2 < d2max;
+    xform_point(J.X, J.src_xyz + 3 * (size_t)k, qx, qy, qz);
+    in = nn_search(J.tgt, qx, qy, qz, d2) >= 0 && (double)d2 < d2max;
   }
   const unsigned m = __ballot_sync(0xffffffffu, in);
-  if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, __popc(m));
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(&counts[blockIdx.y], __popc(m));
 }
 
 // FindCorrespondence search (CorresApp.cpp:145-161): match[k] = original target index or -1
-__global__ void __launch_bounds__(kThreads) correspond_kernel(GridDev g, const float* __restrict__ src_xyz,
-                                                              const float* __restrict__ src_nrm, int n, XformD X,
-                                                              double d2max, double ncos, int* __restrict__ match,
-                                                              int* __restrict__ cta_count) {
+__global__ void __launch_bounds__(kThreads) correspond_kernel(const CorrJob* __restrict__ jobs, double d2max, double ncos) {
+  const CorrJob& J = jobs[blockIdx.y];
+  if ((int)blockIdx.x >= J.nblk) return;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   int mt = -1;
-  if (k < n) {
+  if (k < J.n) {
     float qx, qy, qz, d2;
-    xform_point(X, src_xyz + 3 * (size_t)k, qx, qy, qz);
-    const int m = nn_search(g, qx, qy, qz, d2);
+    xform_point(J.X, J.src_xyz + 3 * (size_t)k, qx, qy, qz);
+    const int m = nn_search(J.tgt, qx, qy, qz, d2);
     if (m >= 0 && (double)d2 < d2max) {
       float nx, ny, nz;
-      xform_normal(X, src_nrm + 3 * (size_t)k, nx, ny, nz);
-      const float4 tn = __ldg(&g.nrm[m]);
+      xform_normal(J.X, J.src_nrm + 3 * (size_t)k, nx, ny, nz);
+      const float4 tn = __ldg(&J.tgt.nrm[m]);
       const float dot = __fadd_rn(__fadd_rn(__fmul_rn(tn.x, nx), __fmul_rn(tn.y, ny)), __fmul_rn(tn.z, nz));   // NormalDot
-      if ((double)dot > ncos) mt = __float_as_int(__ldg(&g.pts[m]).w);
+      if ((double)dot > ncos) mt = __float_as_int(__ldg(&J.tgt.pts[m]).w);
     }
-    match[k] = mt;
+    J.match[k] = mt;
   }
   const int c = __syncthreads_count(mt >= 0);
-  if (threadIdx.x == 0) cta_count[blockIdx.x] = c;
+  if (threadIdx.x == 0) J.cta_count[blockIdx.x] = c;
 }
 
-// exclusive scan of the per-CTA counts (a few hundred entries) by one CTA; total -> offsets[nblk]
-__global__ void scan_counts_kernel(const int* __restrict__ counts, int* __restrict__ offsets, int nblk) {
+// exclusive scan of one pair's per-CTA counts (a few hundred to a few thousand entries) by one CTA; total -> offsets[nblk]
+// and totals[pair]
+__global__ void scan_counts_kernel(const CorrJob* __restrict__ jobs, long long* __restrict__ totals) {
+  const CorrJob& J = jobs[blockIdx.x];
+  const int nblk = J.nblk;
+  const int* counts = J.cta_count;
+  int* offsets = J.offsets;
   __shared__ int s_carry;
   __shared__ int s_w[32];
   if (threadIdx.x == 0) s_carry = 0;
@@ -522,18 +571,30 @@ __global__ void scan_counts_kernel(const int* __restrict__ counts, int* __restri
     if (threadIdx.x == blockDim.x - 1) s_carry = incl;
     __syncthreads();
   }
-  if (threadIdx.x == 0) offsets[nblk] = s_carry;
+  if (threadIdx.x == 0) { offsets[nblk] = s_carry; totals[blockIdx.x] = s_carry; }
+}
+
+// first output row of every pair: exclusive prefix of the totals (bases[npairs] = grand total)
+__global__ void pair_base_kernel(const long long* __restrict__ totals, long long* __restrict__ bases, int npairs) {
+  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+  long long acc = 0;
+  for (int p = 0; p < npairs; p++) { bases[p] = acc; acc += totals[p]; }
+  bases[npairs] = acc;
 }
 
 // ordered compaction (ascending source index, CorresApp.cpp:157) + information matrix sums (CorresApp.cpp:186-208)
-__global__ void __launch_bounds__(kThreads) compact_kernel(const int* __restrict__ match, const int* __restrict__ offsets,
-                                                           const float* __restrict__ src_xyz, int n, int32_t* __restrict__ pairs,
-                                                           size_t cap, double* __restrict__ info_acc) {
+__global__ void __launch_bounds__(kThreads) compact_kernel(const CorrJob* __restrict__ jobs, const long long* __restrict__ bases,
+                                                           int32_t* __restrict__ pairs, long long cap) {
+  const CorrJob& J = jobs[blockIdx.y];
+  if ((int)blockIdx.x >= J.nblk) return;
+  const int n = J.n;
+  const float* src_xyz = J.src_xyz;
+  double* info_acc = J.info;
   __shared__ int s_w[kThreads / 32];
   __shared__ double s_acc[kThreads / 32][12];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int mt = (k < n) ? match[k] : -1;
+  const int mt = (k < n) ? J.match[k] : -1;
   const unsigned bal = __ballot_sync(0xffffffffu, mt >= 0);
   if (lane == 0) s_w[w] = __popc(bal);
   __syncthreads();
@@ -543,7 +604,7 @@ __global__ void __launch_bounds__(kThreads) compact_kernel(const int* __restrict
 #pragma unroll
   for (int i = 0; i < 12; i++) acc[i] = 0.0;
   if (mt >= 0) {
-    const size_t pos = (size_t)offsets[blockIdx.x] + before + __popc(bal & ((1u << lane) - 1));
+    const long long pos = bases[blockIdx.y] + (long long)J.offsets[blockIdx.x] + before + __popc(bal & ((1u << lane) - 1));
     if (pairs && pos < cap) { pairs[2 * pos] = mt; pairs[2 * pos + 1] = k; }
     if (info_acc) {
       // A = [I | 0 2sz -2sy; -2sz 0 2sx; 2sy -2sx 0]; entry (r,c) of A^T A = (A0r*A0c + A1r*A1c) + A2r*A2c in double
@@ -617,12 +678,73 @@ __global__ void __launch_bounds__(256) grid_scatter_kernel(const float* __restri
   snrm[pos] = make_float4(nrm[3 * (size_t)i], nrm[3 * (size_t)i + 1], nrm[3 * (size_t)i + 2], 0.0f);
 }
 
+
+// puts the points of every cell in ascending original index (insertion sort; a cell holds a handful of points), so that
+// the sorted layout -- which is also the order in which the source role feeds the normal equations -- does not depend
+// on the order in which the scatter's atomics were served: results are reproducible run to run
+__global__ void __launch_bounds__(256) grid_order_cells_kernel(const int* __restrict__ cell_start, size_t ncell,
+                                                               float4* __restrict__ pts, float4* __restrict__ nrm) {
+  const size_t c = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  const int s0 = cell_start[c], s1 = cell_start[c + 1];
+  for (int i = s0 + 1; i < s1; i++) {
+    const float4 p = pts[i], q = nrm[i];
+    const int key = __float_as_int(p.w);
+    int j = i - 1;
+    while (j >= s0 && __float_as_int(pts[j].w) > key) { pts[j + 1] = pts[j]; nrm[j + 1] = nrm[j]; j--; }
+    pts[j + 1] = p; nrm[j + 1] = q;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
+// Per-device context: the ICP stream and an arena of device / pinned-host buffers that persists across calls (the
+// working copies of one 1225-pair batch are 2.9 GB: allocating and freeing them inside every call cost tens of
+// milliseconds of host time inside the caller's timed region and made the placement of that memory -- and with it
+// the throughput of a latency-bound gather kernel -- differ from call to call).
+// ---------------------------------------------------------------------------------------------
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    const size_t want = (bytes + (bytes >> 3) + 4095) & ~(size_t)4095;       // 12 % head room: sizes vary a little
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) { cudaGetLastError(); e = cudaMalloc(&p, bytes); if (e == cudaSuccess) cap = bytes; return e; }
+    cap = want;
+    return cudaSuccess;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+struct HostBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    const size_t want = (bytes + (bytes >> 2) + 4095) & ~(size_t)4095;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
+
 struct IcpCtx {
   int device = 0;
   cudaStream_t stream = nullptr;
   cudaEvent_t events[kMaxEvents] = {};
   uint64_t launches = 0;
+  std::mutex op_mu;                 // one batched operation at a time per device (they share the arena)
+  DevBuf cur, part, state;          // align: working copies, CTA partials, PairState[]
+  DevBuf jobs, match, counts, offsets, pairs, info, totals;   // gate / correspondence passes
+  HostBuf h_state, h_jobs, h_small;
+  void release() {
+    cur.release(); part.release(); state.release(); jobs.release(); match.release(); counts.release(); offsets.release();
+    pairs.release(); info.release(); totals.release(); h_state.release(); h_jobs.release(); h_small.release();
+  }
 };
 std::mutex g_ctx_mu;
 std::map<int, IcpCtx*> g_ctx;
@@ -638,6 +760,11 @@ IcpCtx* get_ctx(int device) {
   for (int i = 0; i < kMaxEvents; i++) cudaEventCreate(&c->events[i]);
   g_ctx[device] = c;
   return c;
+}
+
+int cuda_fail(const char* what, cudaError_t e) {
+  er::set_error("%s: %s", what, cudaGetErrorString(e));
+  return ER_ERR_CUDA;
 }
 
 }  // namespace
@@ -658,7 +785,9 @@ struct er_cloud {
 extern "C" {
 
 er_cloud* er_cloud_upload(int device, const float* xyz, const float* normals, size_t n, double cell_size) {
-  if (!xyz || !normals || !(cell_size > 0)) { er::set_error("er_cloud_upload: bad arguments"); return nullptr; }
+  // an empty fragment (a file that failed to load, or whose normals are all NaN: CorresApp.cpp:93-98 keeps going) is a
+  // valid cloud; its buffers may be null
+  if ((n > 0 && (!xyz || !normals)) || !(cell_size > 0)) { er::set_error("er_cloud_upload: bad arguments"); return nullptr; }
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
     er::set_error("er_cloud_upload: CUDA device %d not available (%d devices); this library has no CPU path", device, ndev);
@@ -687,11 +816,13 @@ er_cloud* er_cloud_upload(int device, const float* xyz, const float* normals, si
   const int* dim = g.dim;
   const size_t ncell = (size_t)dim[0] * dim[1] * dim[2];
   // one device allocation: sorted points and normals, the original-order copies, the cell table (+1 cursor slot),
-  // and the build's scratch (cell of every point, scan workspace)
-  IcpCtx* ctx = get_ctx(device);
+  // and the build's scratch (cell of every point, scan workspace).  Uploads may run from several host threads at once
+  // (CorresApp.cpp:82 loads the fragments from an OpenMP loop): each builds on a stream of its own.
   cudaError_t e = cudaSetDevice(device);
+  cudaStream_t st = nullptr;
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking);
   size_t scan_bytes = 0;
-  if (e == cudaSuccess) e = cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (int*)nullptr, (int*)nullptr, (int)(ncell + 2), ctx->stream);
+  if (e == cudaSuccess) e = cub::DeviceScan::InclusiveSum(nullptr, scan_bytes, (int*)nullptr, (int*)nullptr, (int)(ncell + 2), st);
   auto up256 = [](size_t b) { return (b + 255) & ~(size_t)255; };
   const size_t o_pts = 0, o_nrm = o_pts + up256(sizeof(float4) * n), o_xyz = o_nrm + up256(sizeof(float4) * n),
                o_no = o_xyz + up256(sizeof(float) * 3 * n), o_A = o_no + up256(sizeof(float) * 3 * n),
@@ -707,21 +838,23 @@ er_cloud* er_cloud_upload(int device, const float* xyz, const float* normals, si
     void* d_scan = base + o_scan;
     g.pts = c->d_pts; g.nrm = c->d_nrm; g.cell_start = c->d_cell_start;
     g.xyz_orig = c->d_xyz; g.nrm_orig = c->d_nrm_orig;
-    if (n) e = cudaMemcpyAsync(c->d_xyz, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess && n) e = cudaMemcpyAsync(c->d_nrm_orig, normals, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_cell_start, 0, sizeof(int) * (ncell + 2), ctx->stream);
+    if (n) e = cudaMemcpyAsync(c->d_xyz, xyz, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(c->d_nrm_orig, normals, sizeof(float) * 3 * n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemsetAsync(c->d_cell_start, 0, sizeof(int) * (ncell + 2), st);
     if (e == cudaSuccess && n) {
       const int nb = (int)((n + 255) / 256);
-      grid_count_kernel<<<nb, 256, 0, ctx->stream>>>(g, c->d_xyz, (int)n, d_cid, c->d_cell_start);
-      e = cub::DeviceScan::InclusiveSum(d_scan, scan_bytes, c->d_cell_start, c->d_cell_start, (int)(ncell + 2), ctx->stream);
+      grid_count_kernel<<<nb, 256, 0, st>>>(g, c->d_xyz, (int)n, d_cid, c->d_cell_start);
+      e = cub::DeviceScan::InclusiveSum(d_scan, scan_bytes, c->d_cell_start, c->d_cell_start, (int)(ncell + 2), st);
       if (e == cudaSuccess) {
-        grid_scatter_kernel<<<nb, 256, 0, ctx->stream>>>(c->d_xyz, c->d_nrm_orig, (int)n, d_cid, c->d_cell_start, c->d_pts, c->d_nrm);
+        grid_scatter_kernel<<<nb, 256, 0, st>>>(c->d_xyz, c->d_nrm_orig, (int)n, d_cid, c->d_cell_start, c->d_pts, c->d_nrm);
+        grid_order_cells_kernel<<<(unsigned)((ncell + 255) / 256), 256, 0, st>>>(c->d_cell_start, ncell, c->d_pts, c->d_nrm);
         e = cudaGetLastError();
       }
     }
     // the caller's buffers may be reused after return, and build errors belong to this call
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   }
+  if (st) cudaStreamDestroy(st);
   if (e != cudaSuccess) {
     er::set_error("er_cloud_upload: %s", cudaGetErrorString(e));
     er_cloud_free(c);
@@ -739,30 +872,72 @@ void er_cloud_free(er_cloud* c) {
 
 size_t er_cloud_size(const er_cloud* c) { return c ? c->n : 0; }
 
-int er_icp_count_inliers(er_cloud* tgt, er_cloud* src, const double T[16], double dist, int* cnt) {
-  ER_ARG(tgt && src && T && cnt && tgt->device == src->device, "count_inliers: bad arguments");
-  ER_ARG(dist <= tgt->cell, "count_inliers: dist exceeds the target cloud's grid cell size");
-  IcpCtx* ctx = get_ctx(tgt->device);
+int er_icp_release(int device) {
+  IcpCtx* ctx = get_ctx(device);
   ER_ARG(ctx, "no CUDA context");
-  ER_CUDA(cudaSetDevice(tgt->device));
-  int* d_cnt = nullptr;
-  ER_CUDA(cudaMalloc((void**)&d_cnt, sizeof(int)));
-  ER_CUDA(cudaMemsetAsync(d_cnt, 0, sizeof(int), ctx->stream));
-  XformD X;
-  for (int i = 0; i < 12; i++) X.T[i] = T[i];
-  const int n = (int)src->n;
-  if (n > 0) {
-    count_inliers_kernel<<<(n + kThreads - 1) / kThreads, kThreads, 0, ctx->stream>>>(tgt->grid, src->d_xyz, n, X, dist * dist, d_cnt);
-    ctx->launches++;
-  }
-  cudaError_t e = cudaMemcpyAsync(cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_cnt);
-  if (e != cudaSuccess) { er::set_error("count_inliers: %s", cudaGetErrorString(e)); return ER_ERR_CUDA; }
+  std::lock_guard<std::mutex> lk(ctx->op_mu);
+  ER_CUDA(cudaSetDevice(device));
+  ER_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->release();
   return ER_OK;
 }
 
-static int align_chunk(er_cloud* const* clouds, int nclouds, const int* tgt_idx, const int* src_idx, int npairs,
+// ---- gate
+int er_icp_count_inliers_batch(er_cloud* const* clouds, int nclouds, const int* tgt_idx, const int* src_idx, int npairs,
+                               const double* T, double dist, int* cnt) {
+  ER_ARG(clouds && nclouds > 0 && tgt_idx && src_idx && npairs >= 0 && T && cnt, "count_inliers_batch: bad arguments");
+  if (npairs == 0) return ER_OK;
+  ER_ARG(clouds[0], "count_inliers_batch: null cloud");
+  const int device = clouds[0]->device;
+  IcpCtx* ctx = get_ctx(device);
+  ER_ARG(ctx, "no CUDA context");
+  std::lock_guard<std::mutex> lk(ctx->op_mu);
+  ER_CUDA(cudaSetDevice(device));
+  cudaError_t e = ctx->h_jobs.ensure(sizeof(GateJob) * (size_t)npairs);
+  if (e == cudaSuccess) e = ctx->jobs.ensure(sizeof(GateJob) * (size_t)npairs);
+  if (e == cudaSuccess) e = ctx->counts.ensure(sizeof(int) * (size_t)npairs);
+  if (e != cudaSuccess) return cuda_fail("count_inliers_batch", e);
+  GateJob* hj = (GateJob*)ctx->h_jobs.p;
+  int max_blk = 0;
+  for (int p = 0; p < npairs; p++) {
+    ER_ARG(tgt_idx[p] >= 0 && tgt_idx[p] < nclouds && src_idx[p] >= 0 && src_idx[p] < nclouds, "count_inliers_batch: cloud index out of range");
+    const er_cloud* t = clouds[tgt_idx[p]];
+    const er_cloud* s = clouds[src_idx[p]];
+    ER_ARG(t && s && t->device == device && s->device == device, "count_inliers_batch: clouds must live on one device");
+    ER_ARG(dist <= t->cell, "count_inliers: dist exceeds the target cloud's grid cell size");
+    hj[p].tgt = t->grid;
+    hj[p].src_xyz = s->d_xyz;
+    hj[p].n = (int)s->n;
+    for (int i = 0; i < 12; i++) hj[p].X.T[i] = T[16 * (size_t)p + i];
+    max_blk = std::max(max_blk, (int)((s->n + kThreads - 1) / kThreads));
+  }
+  e = cudaMemcpyAsync(ctx->jobs.p, hj, sizeof(GateJob) * (size_t)npairs, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(ctx->counts.p, 0, sizeof(int) * (size_t)npairs, ctx->stream);
+  if (e == cudaSuccess && max_blk > 0) {
+    // blockIdx.y is limited to 65535 pairs per launch
+    for (int p0 = 0; p0 < npairs && e == cudaSuccess; p0 += 65535) {
+      const int np = std::min(65535, npairs - p0);
+      count_inliers_kernel<<<dim3((unsigned)max_blk, (unsigned)np), kThreads, 0, ctx->stream>>>((const GateJob*)ctx->jobs.p + p0, dist * dist,
+                                                                                              (int*)ctx->counts.p + p0);
+      ctx->launches++;
+      e = cudaGetLastError();
+    }
+  }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(cnt, ctx->counts.p, sizeof(int) * (size_t)npairs, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return cuda_fail("count_inliers_batch", e);
+  return ER_OK;
+}
+
+int er_icp_count_inliers(er_cloud* tgt, er_cloud* src, const double T[16], double dist, int* cnt) {
+  ER_ARG(tgt && src && T && cnt && tgt->device == src->device, "count_inliers: bad arguments");
+  er_cloud* cl[2] = {tgt, src};
+  const int ti = 0, si = 1;
+  return er_icp_count_inliers_batch(cl, 2, &ti, &si, 1, T, dist, cnt);
+}
+
+// ---- ICP
+static int align_chunk(IcpCtx* ctx, er_cloud* const* clouds, int nclouds, const int* tgt_idx, const int* src_idx, int npairs,
                        const double* Tinit, double max_dist, int max_iter, double eps, int fixed_iters, double* Tout,
                        int* iters, double* fitness);
 
@@ -770,28 +945,30 @@ int er_icp_align_batch(er_cloud* const* clouds, int nclouds, const int* tgt_idx,
                        const double* Tinit, double max_dist, int max_iter, double eps, int fixed_iters, double* Tout,
                        int* iters, double* fitness) {
   ER_ARG(clouds && nclouds > 0 && tgt_idx && src_idx && npairs >= 0 && Tinit && Tout && max_iter >= 1, "align_batch: bad arguments");
+  if (npairs == 0) return ER_OK;
+  ER_ARG(clouds[0], "align_batch: null cloud");
+  IcpCtx* ctx = get_ctx(clouds[0]->device);
+  ER_ARG(ctx, "no CUDA context");
+  std::lock_guard<std::mutex> lk(ctx->op_mu);
   // every pair in flight owns a working copy of its source cloud (12 B per point); ER_ICP_CHUNK bounds that memory
-  // by aligning the list in chunks (each chunk pays its own allocations and a synchronisation)
-  int chunk = npairs > 0 ? npairs : 1;     // measured: 5 chunks of 256 pairs cost 620 ms against 406 ms for one batch of 1225
+  // by aligning the list in chunks (each chunk pays a synchronisation)
+  int chunk = npairs;
   if (const char* ev = std::getenv("ER_ICP_CHUNK")) chunk = std::max(1, std::atoi(ev));             // experiment knob
+  chunk = std::min(chunk, 65535);                                                                    // blockIdx.y
   for (int p0 = 0; p0 < npairs; p0 += chunk) {
     const int n = std::min(chunk, npairs - p0);
-    const int rc = align_chunk(clouds, nclouds, tgt_idx + p0, src_idx + p0, n, Tinit + 16 * (size_t)p0, max_dist, max_iter, eps,
+    const int rc = align_chunk(ctx, clouds, nclouds, tgt_idx + p0, src_idx + p0, n, Tinit + 16 * (size_t)p0, max_dist, max_iter, eps,
                                fixed_iters, Tout + 16 * (size_t)p0, iters ? iters + p0 : nullptr, fitness ? fitness + p0 : nullptr);
     if (rc != ER_OK) return rc;
   }
   return ER_OK;
 }
 
-static int align_chunk(er_cloud* const* clouds, int nclouds, const int* tgt_idx, const int* src_idx, int npairs,
+static int align_chunk(IcpCtx* ctx, er_cloud* const* clouds, int nclouds, const int* tgt_idx, const int* src_idx, int npairs,
                        const double* Tinit, double max_dist, int max_iter, double eps, int fixed_iters, double* Tout,
                        int* iters, double* fitness) {
-  if (npairs == 0) return ER_OK;
-  const int device = clouds[0]->device;
-  IcpCtx* ctx = get_ctx(device);
-  ER_ARG(ctx, "no CUDA context");
+  const int device = ctx->device;
   ER_CUDA(cudaSetDevice(device));
-  std::vector<PairState> st((size_t)npairs);
   size_t cur_floats = 0, part_doubles = 0;
   int max_blocks = 1;
   for (int p = 0; p < npairs; p++) {
@@ -802,15 +979,22 @@ static int align_chunk(er_cloud* const* clouds, int nclouds, const int* tgt_idx,
     ER_ARG(max_dist <= t->cell, "align_batch: max_dist exceeds the target cloud's grid cell size");
     const int nb = std::max(1, (int)((s->n + kPtsPerCta - 1) / kPtsPerCta));
     max_blocks = std::max(max_blocks, nb);
-    cur_floats += 3 * s->n;
+    cur_floats += (3 * s->n + 3) & ~(size_t)3;          // every working copy starts 16-byte aligned
     part_doubles += (size_t)nb * kAcc;
   }
-  float* d_cur = nullptr;
-  double* d_part = nullptr;
-  PairState* d_st = nullptr;
-  ER_CUDA(cudaMalloc((void**)&d_cur, sizeof(float) * std::max<size_t>(cur_floats, 4)));
-  ER_CUDA(cudaMalloc((void**)&d_part, sizeof(double) * part_doubles));
-  ER_CUDA(cudaMalloc((void**)&d_st, sizeof(PairState) * (size_t)npairs));
+  cudaError_t e = ctx->cur.ensure(sizeof(float) * std::max<size_t>(cur_floats, 4));
+  if (e == cudaSuccess) e = ctx->part.ensure(sizeof(double) * part_doubles);
+  if (e == cudaSuccess) e = ctx->state.ensure(sizeof(PairState) * (size_t)npairs);
+  if (e == cudaSuccess) e = ctx->h_state.ensure(sizeof(PairState) * (size_t)npairs);
+  if (e != cudaSuccess) return cuda_fail("align_batch (arena)", e);
+  // the order in which the source points enter the search and the sums: the fragment's cell-sorted order (queries of a
+  // warp are neighbours in space: coherent gathers) unless ER_ICP_SRC_ORDER=file asks for the file order
+  bool sorted_src = true;
+  if (const char* ev = std::getenv("ER_ICP_SRC_ORDER")) sorted_src = std::strcmp(ev, "file") != 0;    // experiment knob
+  PairState* st = (PairState*)ctx->h_state.p;
+  float* d_cur = (float*)ctx->cur.p;
+  double* d_part = (double*)ctx->part.p;
+  PairState* d_st = (PairState*)ctx->state.p;
   size_t co = 0, po = 0;
   int max_rings = 1;
   for (int p = 0; p < npairs; p++) {
@@ -820,17 +1004,18 @@ static int align_chunk(er_cloud* const* clouds, int nclouds, const int* tgt_idx,
     std::memset(&S, 0, sizeof S);
     S.tgt = t->grid;
     S.cur = d_cur + co;
+    S.src4 = sorted_src ? (const er_float4*)s->d_pts : nullptr;
+    S.src3 = s->d_xyz;
     S.n_src = (int)s->n;
     S.nblocks = std::max(1, (int)((s->n + kPtsPerCta - 1) / kPtsPerCta));
     S.partials = d_part + po;
     for (int i = 0; i < 16; i++) S.Tinc[i] = S.fin[i] = (float)Tinit[16 * (size_t)p + i];   // guess.cast<float>()
     S.prev_mse = DBL_MAX;
-    if (s->n) cudaMemcpyAsync(S.cur, s->d_xyz, sizeof(float) * 3 * s->n, cudaMemcpyDeviceToDevice, ctx->stream);
-    co += 3 * s->n;
+    co += (3 * s->n + 3) & ~(size_t)3;
     po += (size_t)S.nblocks * kAcc;
     max_rings = std::max(max_rings, t->grid.rings);
   }
-  cudaError_t e = cudaMemcpyAsync(d_st, st.data(), sizeof(PairState) * (size_t)npairs, cudaMemcpyHostToDevice, ctx->stream);
+  e = cudaMemcpyAsync(d_st, st, sizeof(PairState) * (size_t)npairs, cudaMemcpyHostToDevice, ctx->stream);
   const double max_d2 = max_dist * max_dist;
   // the smallest float that is >= max_d2: no candidate with a larger float distance can pass `(double)d2 > max_d2`
   float bd_init = (float)max_d2;
@@ -842,17 +1027,17 @@ static int align_chunk(er_cloud* const* clouds, int nclouds, const int* tgt_idx,
   if (const char* ev = std::getenv("ER_ICP_MINB")) minb = std::atoi(ev) == 6 ? 6 : 8;              // experiment knob
   const dim3 grid((unsigned)max_blocks, (unsigned)npairs);
   for (int it = 0; it < max_iter && e == cudaSuccess; it++) {
-    if (coop && minb == 8) icp_iter_kernel<true, 8><<<grid, kThreads, 0, ctx->stream>>>(d_st, max_d2, bd_init, max_iter, eps, fixed_iters);
-    else if (coop) icp_iter_kernel<true, 6><<<grid, kThreads, 0, ctx->stream>>>(d_st, max_d2, bd_init, max_iter, eps, fixed_iters);
-    else if (minb == 8) icp_iter_kernel<false, 8><<<grid, kThreads, 0, ctx->stream>>>(d_st, max_d2, bd_init, max_iter, eps, fixed_iters);
-    else icp_iter_kernel<false, 6><<<grid, kThreads, 0, ctx->stream>>>(d_st, max_d2, bd_init, max_iter, eps, fixed_iters);
+    const int first = it == 0;
+    if (coop && minb == 8) icp_iter_kernel<true, 8><<<grid, kThreads, 0, ctx->stream>>>(d_st, max_d2, bd_init, max_iter, eps, fixed_iters, first);
+    else if (coop) icp_iter_kernel<true, 6><<<grid, kThreads, 0, ctx->stream>>>(d_st, max_d2, bd_init, max_iter, eps, fixed_iters, first);
+    else if (minb == 8) icp_iter_kernel<false, 8><<<grid, kThreads, 0, ctx->stream>>>(d_st, max_d2, bd_init, max_iter, eps, fixed_iters, first);
+    else icp_iter_kernel<false, 6><<<grid, kThreads, 0, ctx->stream>>>(d_st, max_d2, bd_init, max_iter, eps, fixed_iters, first);
     ctx->launches++;
     e = cudaGetLastError();
   }
-  if (e == cudaSuccess) e = cudaMemcpyAsync(st.data(), d_st, sizeof(PairState) * (size_t)npairs, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(st, d_st, sizeof(PairState) * (size_t)npairs, cudaMemcpyDeviceToHost, ctx->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d_cur); cudaFree(d_part); cudaFree(d_st);
-  if (e != cudaSuccess) { er::set_error("align_batch: %s", cudaGetErrorString(e)); return ER_ERR_CUDA; }
+  if (e != cudaSuccess) return cuda_fail("align_batch", e);
   for (int p = 0; p < npairs; p++) {
     for (int i = 0; i < 16; i++) Tout[16 * (size_t)p + i] = (double)st[(size_t)p].fin[i];    // .cast<double>(), CorresApp.cpp:312
     if (iters) iters[p] = st[(size_t)p].iters;
@@ -869,59 +1054,124 @@ int er_icp_align(er_cloud* tgt, er_cloud* src, const double Tinit[16], double ma
   return er_icp_align_batch(cl, 2, &ti, &si, 1, Tinit, max_dist, max_iter, eps, fixed_iters, Tout, iters, fitness);
 }
 
+// ---- correspondences
+int er_icp_correspondences_batch(er_cloud* const* clouds, int nclouds, const int* tgt_idx, const int* src_idx, int npairs,
+                                 const double* T, double dist, double normal_cos, int32_t* pairs, size_t cap,
+                                 size_t* row_start, double* info36) {
+  ER_ARG(clouds && nclouds > 0 && tgt_idx && src_idx && npairs >= 0 && T && row_start, "correspondences_batch: bad arguments");
+  row_start[0] = 0;
+  if (npairs == 0) return ER_OK;
+  ER_ARG(clouds[0], "correspondences_batch: null cloud");
+  const int device = clouds[0]->device;
+  IcpCtx* ctx = get_ctx(device);
+  ER_ARG(ctx, "no CUDA context");
+  std::lock_guard<std::mutex> lk(ctx->op_mu);
+  ER_CUDA(cudaSetDevice(device));
+  size_t n_total = 0, blk_total = 0;
+  int max_blk = 0;
+  for (int p = 0; p < npairs; p++) {
+    ER_ARG(tgt_idx[p] >= 0 && tgt_idx[p] < nclouds && src_idx[p] >= 0 && src_idx[p] < nclouds, "correspondences_batch: cloud index out of range");
+    const er_cloud* t = clouds[tgt_idx[p]];
+    const er_cloud* s = clouds[src_idx[p]];
+    ER_ARG(t && s && t->device == device && s->device == device, "correspondences_batch: clouds must live on one device");
+    ER_ARG(dist <= t->cell, "correspondences: dist exceeds the target cloud's grid cell size");
+    const int nblk = (int)((s->n + kThreads - 1) / kThreads);
+    n_total += s->n;
+    blk_total += (size_t)nblk + 1;
+    max_blk = std::max(max_blk, nblk);
+  }
+  const size_t pcap = pairs ? std::min(cap, n_total) : 0;
+  cudaError_t e = ctx->h_jobs.ensure(sizeof(CorrJob) * (size_t)npairs);
+  if (e == cudaSuccess) e = ctx->jobs.ensure(sizeof(CorrJob) * (size_t)npairs);
+  if (e == cudaSuccess) e = ctx->match.ensure(sizeof(int) * std::max<size_t>(n_total, 1));
+  if (e == cudaSuccess) e = ctx->counts.ensure(sizeof(int) * blk_total);
+  if (e == cudaSuccess) e = ctx->offsets.ensure(sizeof(int) * blk_total);
+  if (e == cudaSuccess) e = ctx->totals.ensure(sizeof(long long) * (2 * (size_t)npairs + 1));
+  if (e == cudaSuccess) e = ctx->info.ensure(sizeof(double) * 13 * (size_t)npairs);
+  if (e == cudaSuccess && pcap) e = ctx->pairs.ensure(sizeof(int32_t) * 2 * pcap);
+  if (e == cudaSuccess) e = ctx->h_small.ensure((sizeof(long long) * (2 * (size_t)npairs + 1)) + sizeof(double) * 13 * (size_t)npairs);
+  if (e != cudaSuccess) return cuda_fail("correspondences_batch (arena)", e);
+  CorrJob* hj = (CorrJob*)ctx->h_jobs.p;
+  size_t no = 0, bo = 0;
+  for (int p = 0; p < npairs; p++) {
+    const er_cloud* t = clouds[tgt_idx[p]];
+    const er_cloud* s = clouds[src_idx[p]];
+    CorrJob& J = hj[p];
+    J.tgt = t->grid;
+    J.src_xyz = s->d_xyz;
+    J.src_nrm = s->d_nrm_orig;
+    J.n = (int)s->n;
+    J.nblk = (int)((s->n + kThreads - 1) / kThreads);
+    for (int i = 0; i < 12; i++) J.X.T[i] = T[16 * (size_t)p + i];
+    J.match = (int*)ctx->match.p + no;
+    J.cta_count = (int*)ctx->counts.p + bo;
+    J.offsets = (int*)ctx->offsets.p + bo;
+    J.info = info36 ? (double*)ctx->info.p + 13 * (size_t)p : nullptr;
+    no += s->n;
+    bo += (size_t)J.nblk + 1;
+  }
+  long long* d_totals = (long long*)ctx->totals.p;
+  long long* d_bases = d_totals + npairs;
+  e = cudaMemcpyAsync(ctx->jobs.p, hj, sizeof(CorrJob) * (size_t)npairs, cudaMemcpyHostToDevice, ctx->stream);
+  if (e == cudaSuccess && info36) e = cudaMemsetAsync(ctx->info.p, 0, sizeof(double) * 13 * (size_t)npairs, ctx->stream);
+  const CorrJob* dj = (const CorrJob*)ctx->jobs.p;
+  if (e == cudaSuccess) {
+    if (max_blk > 0)
+      for (int p0 = 0; p0 < npairs; p0 += 65535)
+        correspond_kernel<<<dim3((unsigned)max_blk, (unsigned)std::min(65535, npairs - p0)), kThreads, 0, ctx->stream>>>(dj + p0, dist * dist, normal_cos);
+    scan_counts_kernel<<<(unsigned)npairs, 256, 0, ctx->stream>>>(dj, d_totals);
+    pair_base_kernel<<<1, 32, 0, ctx->stream>>>(d_totals, d_bases, npairs);
+    if (max_blk > 0)
+      for (int p0 = 0; p0 < npairs; p0 += 65535)
+        compact_kernel<<<dim3((unsigned)max_blk, (unsigned)std::min(65535, npairs - p0)), kThreads, 0, ctx->stream>>>(
+            dj + p0, d_bases + p0, (int32_t*)(pcap ? ctx->pairs.p : nullptr), (long long)pcap);
+    ctx->launches += 4;
+    e = cudaGetLastError();
+  }
+  long long* h_bases = (long long*)ctx->h_small.p;
+  double* h_info = (double*)(h_bases + 2 * (size_t)npairs + 1);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(h_bases, d_bases, sizeof(long long) * ((size_t)npairs + 1), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && info36) e = cudaMemcpyAsync(h_info, ctx->info.p, sizeof(double) * 13 * (size_t)npairs, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) return cuda_fail("correspondences_batch", e);
+  for (int p = 0; p <= npairs; p++) row_start[p] = (size_t)h_bases[p];
+  const size_t total = (size_t)h_bases[npairs];
+  if (pairs && total > 0) {
+    const size_t m = std::min(total, pcap);
+    if (m) ER_CUDA(cudaMemcpy(pairs, ctx->pairs.p, sizeof(int32_t) * 2 * m, cudaMemcpyDeviceToHost));
+  }
+  if (info36) {
+    for (int p = 0; p < npairs; p++) {
+      const double* acc = h_info + 13 * (size_t)p;
+      double* I = info36 + 36 * (size_t)p;
+      std::memset(I, 0, sizeof(double) * 36);
+      I[0] = I[7] = I[14] = acc[0];
+      I[0 * 6 + 4] = I[4 * 6 + 0] = acc[1];  I[0 * 6 + 5] = I[5 * 6 + 0] = acc[2];
+      I[1 * 6 + 3] = I[3 * 6 + 1] = acc[3];  I[1 * 6 + 5] = I[5 * 6 + 1] = acc[4];
+      I[2 * 6 + 3] = I[3 * 6 + 2] = acc[5];  I[2 * 6 + 4] = I[4 * 6 + 2] = acc[6];
+      I[3 * 6 + 3] = acc[7];  I[3 * 6 + 4] = I[4 * 6 + 3] = acc[8];  I[3 * 6 + 5] = I[5 * 6 + 3] = acc[9];
+      I[4 * 6 + 4] = acc[10]; I[4 * 6 + 5] = I[5 * 6 + 4] = acc[11];
+      I[5 * 6 + 5] = acc[12];
+    }
+  }
+  if (pairs && total > cap) {
+    er::set_error("correspondences_batch: %zu rows do not fit the caller's %zu (row_start is filled; retry with a larger buffer)", total, cap);
+    return ER_ERR_CAPACITY;
+  }
+  return ER_OK;
+}
+
 int er_icp_correspondences(er_cloud* tgt, er_cloud* src, const double T[16], double dist, double normal_cos, int32_t* pairs,
                            size_t cap, size_t* n_out, double info36[36]) {
   ER_ARG(tgt && src && T && n_out && tgt->device == src->device, "correspondences: bad arguments");
-  ER_ARG(dist <= tgt->cell, "correspondences: dist exceeds the target cloud's grid cell size");
-  IcpCtx* ctx = get_ctx(tgt->device);
-  ER_ARG(ctx, "no CUDA context");
-  ER_CUDA(cudaSetDevice(tgt->device));
-  const int n = (int)src->n;
+  er_cloud* cl[2] = {tgt, src};
+  const int ti = 0, si = 1;
+  size_t rs[2] = {0, 0};
   *n_out = 0;
-  if (info36) std::memset(info36, 0, sizeof(double) * 36);
-  if (n == 0) return ER_OK;
-  const int nblk = (n + kThreads - 1) / kThreads;
-  int *d_match = nullptr, *d_counts = nullptr, *d_off = nullptr;
-  int32_t* d_pairs = nullptr;
-  double* d_info = nullptr;
-  ER_CUDA(cudaMalloc((void**)&d_match, sizeof(int) * (size_t)n));
-  ER_CUDA(cudaMalloc((void**)&d_counts, sizeof(int) * (size_t)nblk));
-  ER_CUDA(cudaMalloc((void**)&d_off, sizeof(int) * (size_t)(nblk + 1)));
-  const size_t pcap = pairs ? std::min(cap, (size_t)n) : 0;
-  if (pcap) ER_CUDA(cudaMalloc((void**)&d_pairs, sizeof(int32_t) * 2 * pcap));
-  if (info36) {
-    ER_CUDA(cudaMalloc((void**)&d_info, sizeof(double) * 13));
-    ER_CUDA(cudaMemsetAsync(d_info, 0, sizeof(double) * 13, ctx->stream));
-  }
-  XformD X;
-  for (int i = 0; i < 12; i++) X.T[i] = T[i];
-  correspond_kernel<<<nblk, kThreads, 0, ctx->stream>>>(tgt->grid, src->d_xyz, src->d_nrm_orig, n, X, dist * dist, normal_cos,
-                                                        d_match, d_counts);
-  scan_counts_kernel<<<1, 256, 0, ctx->stream>>>(d_counts, d_off, nblk);
-  compact_kernel<<<nblk, kThreads, 0, ctx->stream>>>(d_match, d_off, src->d_xyz, n, d_pairs, pcap, d_info);
-  ctx->launches += 3;
-  cudaError_t e = cudaGetLastError();
-  int total = 0;
-  double acc[13];
-  if (e == cudaSuccess) e = cudaMemcpyAsync(&total, d_off + nblk, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess && info36) e = cudaMemcpyAsync(acc, d_info, sizeof acc, cudaMemcpyDeviceToHost, ctx->stream);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  if (e == cudaSuccess && pcap && total > 0)
-    e = cudaMemcpy(pairs, d_pairs, sizeof(int32_t) * 2 * std::min((size_t)total, pcap), cudaMemcpyDeviceToHost);
-  cudaFree(d_match); cudaFree(d_counts); cudaFree(d_off); cudaFree(d_pairs); cudaFree(d_info);
-  if (e != cudaSuccess) { er::set_error("correspondences: %s", cudaGetErrorString(e)); return ER_ERR_CUDA; }
-  *n_out = (size_t)total;
-  if (info36) {
-    double* I = info36;
-    I[0] = I[7] = I[14] = acc[0];
-    I[0 * 6 + 4] = I[4 * 6 + 0] = acc[1];  I[0 * 6 + 5] = I[5 * 6 + 0] = acc[2];
-    I[1 * 6 + 3] = I[3 * 6 + 1] = acc[3];  I[1 * 6 + 5] = I[5 * 6 + 1] = acc[4];
-    I[2 * 6 + 3] = I[3 * 6 + 2] = acc[5];  I[2 * 6 + 4] = I[4 * 6 + 2] = acc[6];
-    I[3 * 6 + 3] = acc[7];  I[3 * 6 + 4] = I[4 * 6 + 3] = acc[8];  I[3 * 6 + 5] = I[5 * 6 + 3] = acc[9];
-    I[4 * 6 + 4] = acc[10]; I[4 * 6 + 5] = I[5 * 6 + 4] = acc[11];
-    I[5 * 6 + 5] = acc[12];
-  }
-  return ER_OK;
+  const int rc = er_icp_correspondences_batch(cl, 2, &ti, &si, 1, T, dist, normal_cos, pairs, cap, rs, info36);
+  *n_out = rs[1];
+  // the single-pair call keeps its old contract: more rows than `cap` is not an error, n reports how many there are
+  return rc == ER_ERR_CAPACITY ? ER_OK : rc;
 }
 
 int er_icp_event_record(int device, int slot) {

@@ -47,12 +47,12 @@ def make_pose(R, t):
     return T
 
 
-def loop_trajectory(n: int) -> np.ndarray:
-    """Rigid loop inside the 3 m room, looking outward.  Returns [n,4,4]."""
+def loop_trajectory(n: int, center=(1.5, 1.5, 1.5), radius: float = 0.4, bob: float = 0.1) -> np.ndarray:
+    """Rigid loop inside the room (default: the 3 m room of SURVEY 8d), looking outward.  Returns [n,4,4]."""
     out = np.empty((n, 4, 4), dtype=np.float64)
     for i in range(n):
         th = 2.0 * math.pi * i / n
-        c = np.array([1.5 + 0.4 * math.cos(th), 1.5 + 0.1 * math.sin(2 * th), 1.5 + 0.4 * math.sin(th)])
+        c = np.array([center[0] + radius * math.cos(th), center[1] + bob * math.sin(2 * th), center[2] + radius * math.sin(th)])
         # camera z axis (viewing direction) points outward from the room centre in the xz plane
         yaw = math.atan2(math.cos(th), math.sin(th))  # z-axis -> (cos th, 0, sin th)
         R = rot_y(yaw) @ rot_x(0.1 * math.sin(3 * th))

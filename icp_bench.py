@@ -15,12 +15,13 @@ import time
 
 import numpy as np
 
-from . import capi, sharding, synth
+from elasticreconstruction_b200 import capi, sharding, synth
 
 NUM_FRAGMENTS = 50
 POINTS = 200_000
 ITERS = 20
-WARMUP_PASSES = 3        # untimed passes over the whole share before the timed one
+WARMUP_PASSES = 3        # untimed passes over the whole share before the timed ones
+TIMED_PASSES = 5
 REG_DIST = 0.03
 
 
@@ -28,8 +29,82 @@ def all_pairs(n):
     return [(i, j) for i in range(n) for j in range(i + 1, n)]
 
 
+ROOT = os.path.dirname(os.path.abspath(__file__))
+WORKLOAD = "pairwise ICP: %d synthetic fragments ~%dk pts, all %d pairs x %d fixed iterations (BASELINE configs[2])"
+
+
+def _oracle():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    pyoracle.build()
+    return pyoracle
+
+
+def cpu_port_pairs(frags, pairs, Tinit, threads: int):
+    """The CPU port of the path (restated PCL 1.7 ICP inside the reference's omp-parallel-over-pairs loop,
+    CorresApp.cpp:220) on `pairs`; returns (seconds, iterations, poses).  The grids of the fragments involved are built
+    outside the timed part, like the reference's kd-trees are not (CorresApp.cpp:253 builds one per pair) -- a bias in the
+    CPU's favour."""
+    pyoracle = _oracle()
+    used = sorted(set(a for a, _ in pairs) | set(b for _, b in pairs))
+    remap = {f: q for q, f in enumerate(used)}
+    oclouds = [pyoracle.OracleCloud(frags[f][0], frags[f][1], REG_DIST) for f in used]
+    t0 = time.perf_counter()
+    To, ito, _ = pyoracle.icp_align_batch(oclouds, [remap[a] for a, _ in pairs], [remap[b] for _, b in pairs], Tinit,
+                                          REG_DIST, ITERS, 1e-6, True, threads=threads)
+    return time.perf_counter() - t0, ito, To
+
+
+def run_reference(args):
+    """bench.py --impl reference --metric icp: the CPU port on bounded samples of configs[2], all host threads the
+    reference's loop can use (it hard-codes 8).  The true BuildCorrespondence binary needs PCL + FLANN + Boost and cannot
+    be built here."""
+    import json
+    nfrag, points = args.icp_fragments, args.icp_points
+    pairs = all_pairs(nfrag)
+    per = args.ref_pairs_per_step
+    nsteps = args.warmup + args.steps
+    sel = [pairs[(k * 37) % len(pairs)] for k in range(per * nsteps)]          # spread over the list, deterministic
+    used = sorted(set(a for a, _ in sel) | set(b for _, b in sel))
+    frags = {f: synth.make_local_fragment(f, points) for f in used}
+    threads = min(8, os.cpu_count() or 1)
+    step_s, its = [], 0
+    for s in range(nsteps):
+        chunk = sel[s * per:(s + 1) * per]
+        Ti = np.array([synth.pair_init(i, j) for (i, j) in chunk])
+        sec, ito, _ = cpu_port_pairs(frags, chunk, Ti, threads)
+        if s >= args.warmup:
+            step_s.append(sec)
+            its += int(ito.sum())
+    total = float(sum(step_s))
+    value = its / total
+    line = {"impl": "reference", "metric": "fragment-pair ICP iterations/sec", "value": value, "unit": "pair-iterations/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 points, f64 normal equations",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD % (nfrag, points // 1000, len(pairs), ITERS), "pairs_per_step": per, "threads": threads,
+                       "host_cores": os.cpu_count()},
+            "cpu_baseline": {"value": value, "unit": "pair-iterations/s", "cores": threads, "kind": "port",
+                             "sample": "%d steps x %d pairs x %d iterations of the 1225-pair list; restated PCL-1.7 ICP (oracle/"
+                                       "icp_oracle.c) in the reference's omp-parallel-over-pairs loop" % (args.steps, per, ITERS)},
+            "e2e": {"value": value, "unit": "pair-iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+def as_line(icp: dict, args, world: int) -> dict:
+    """The ICP leg as a bench line of its own (bench.py --metric icp)."""
+    return {"metric": icp["metric"], "value": icp["value"], "unit": icp["unit"], "n_gpus": world, "steps": 1,
+            "warmup": icp["warmup_passes"], "ms_per_step": icp["ms"], "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32 points, f64 normal equations", "data": "synthetic", "config": icp["config"],
+            "roofline": icp["roofline"], "cpu_baseline": icp["cpu_baseline"], "e2e": icp["e2e"], "gpu_launches": icp["gpu_launches"],
+            "clocks": icp["clocks"], "passes_ms": icp.get("passes_ms"), "max_pose_error_vs_truth": icp["max_pose_error_vs_truth"],
+            "max_pose_diff_vs_oracle": icp.get("max_pose_diff_vs_oracle")}
+
+
 def _traffic_per_pair_iteration():
-    p = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
+    p = os.path.join(ROOT, "profiles", "traffic.json")
     try:
         import json
         t = json.load(open(p))["icp_iter_kernel"]
@@ -71,12 +146,18 @@ def run(local: int, rank: int, world: int, barrier, peak_gbs: float = 0.0, cpu_p
     sampler = clock_sampler(local) if clock_sampler else None
     if sampler:
         sampler.start()
-    l0 = capi.icp_launch_count(local)
-    capi.icp_event_record(local, 0)
-    T, its, fit = capi.icp_align_batch(clouds, tgt, src, Tinit, REG_DIST, ITERS, 1e-6, True)
-    capi.icp_event_record(local, 1)
-    ms = capi.icp_event_elapsed_ms(local, 0, 1)
-    launches = capi.icp_launch_count(local) - l0
+    # TIMED_PASSES passes over the whole share, each bracketed by device events; the value is the MEDIAN pass (a single
+    # pass was bimodal in round 1 -- see profiles/r2_notes.md), min and max are reported beside it
+    passes = []
+    launches = 0
+    for _ in range(TIMED_PASSES):
+        l0 = capi.icp_launch_count(local)
+        capi.icp_event_record(local, 0)
+        T, its, fit = capi.icp_align_batch(clouds, tgt, src, Tinit, REG_DIST, ITERS, 1e-6, True)
+        capi.icp_event_record(local, 1)
+        passes.append(capi.icp_event_elapsed_ms(local, 0, 1))
+        launches = capi.icp_launch_count(local) - l0
+    ms = float(np.median(passes))
     clocks = sampler.stop() if sampler else None
     barrier()
     t = torch.tensor([ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
@@ -98,11 +179,11 @@ def run(local: int, rank: int, world: int, barrier, peak_gbs: float = 0.0, cpu_p
                         for k, (i, j) in enumerate(mine)])) if len(mine) else 0.0
     res = {
         "metric": "fragment-pair ICP iterations/sec", "value": value, "unit": "pair-iterations/s",
-        "config": {"workload": "pairwise ICP: %d synthetic fragments ~%dk pts, all %d pairs x %d fixed iterations "
-                               "(BASELINE configs[2])" % (num_fragments, points // 1000, len(pairs), ITERS),
+        "config": {"workload": WORKLOAD % (num_fragments, points // 1000, len(pairs), ITERS),
                    "sharding": "pairs round-robin over %d rank(s)" % world, "max_dist": REG_DIST},
         "ms": float(t[0].item()), "pair_iterations": total_iters, "gpu_launches": int(launches),
-        "warmup_passes": WARMUP_PASSES, "clocks": clocks,
+        "warmup_passes": WARMUP_PASSES, "timed_passes": TIMED_PASSES, "passes_ms": [round(float(x), 3) for x in passes],
+        "passes_max_over_min": float(max(passes) / min(passes)), "clocks": clocks,
         "e2e": {"value": total_iters / (float(t[1].item()) * 1e-3), "unit": "pair-iterations/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(len(mine) * 136),
                 "note": "first call in the process: includes the upload of all %d fragments (H2D + device-side grid "
@@ -116,19 +197,9 @@ def run(local: int, rank: int, world: int, barrier, peak_gbs: float = 0.0, cpu_p
         "cpu_baseline": None,
     }
     if rank == 0 and world == 1 and cpu_pairs > 0:
-        root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-        sys.path.insert(0, os.path.join(root, "oracle"))
-        import pyoracle
-        pyoracle.build()
         k = min(cpu_pairs, len(mine))
-        used = sorted(set(tgt[:k]) | set(src[:k]))
-        remap = {f: q for q, f in enumerate(used)}
-        oclouds = [pyoracle.OracleCloud(frags[f][0], frags[f][1], REG_DIST) for f in used]
         threads = min(8, os.cpu_count() or 1)
-        t0 = time.perf_counter()
-        To, ito, _ = pyoracle.icp_align_batch(oclouds, [remap[a] for a in tgt[:k]], [remap[b] for b in src[:k]], Tinit[:k],
-                                              REG_DIST, ITERS, 1e-6, True, threads=threads)
-        cpu_s = time.perf_counter() - t0
+        cpu_s, ito, To = cpu_port_pairs(dict(enumerate(frags)), mine[:k], Tinit[:k], threads)
         res["cpu_baseline"] = {"value": float(ito.sum()) / cpu_s, "unit": "pair-iterations/s", "cores": threads, "kind": "port",
                                "sample": "%d of the %d pairs x %d iterations; restated PCL-1.7 oracle inside the reference's "
                                          "omp-parallel-over-pairs loop (CorresApp.cpp:220); the true binary needs PCL" % (

@@ -49,6 +49,11 @@ const char* er_build_arch(void);
 void er_mat4_mul(const double a[16], const double b[16], double out[16]);
 void er_mat4_inverse(const double m[16], double out[16]);      /* Matrix4d::inverse(), TSDFVolume.cpp:40 */
 
+/* Page-locked host memory for frame buffers handed to the *_batch calls: host->device copies from pageable memory are
+ * staged by the driver at a fraction of the link rate.  (The reference keeps frames in std::vector, IntegrateApp.h.) */
+void* er_host_alloc(size_t bytes);
+void er_host_free(void* p);
+
 /* ================================================================================================
  * TSDF volume  (class TSDFVolume, Integrate/TSDFVolume.h:14-69)
  * ============================================================================================== */
@@ -91,10 +96,19 @@ int er_tsdf_integrate_ctr(er_tsdf* v, const uint16_t* depth, const double Ti[16]
  * er_tsdf_integrate_batch: this is how the 5000-frame ControlGrid configuration is fed. */
 int er_tsdf_integrate_ctr_batch(er_tsdf* v, const uint16_t* depth, const double* Ti, const double T0[16],
                                 const double A0[16], const double* Ai, const int* chunk, int nframes);
+/* The same with the frames already resident in HBM (d_depth is a device pointer), and the device time of the
+ * re-projection alone over those frames (reproject_kernel + z-buffer reset/convert, event-bracketed, milliseconds). */
+int er_tsdf_integrate_ctr_device(er_tsdf* v, const uint16_t* d_depth, const double* Ti, const double T0[16],
+                                 const double A0[16], const double* Ai, const int* chunk, int nframes);
+int er_tsdf_profile_reproject_device(er_tsdf* v, const uint16_t* d_depth, const double* Ti, const double T0[16],
+                                     const double A0[16], const double* Ai, const int* chunk, int nframes, float* ms);
 /* nframes consecutive frames from host memory (depth = nframes*rows*cols, T = nframes*16), in order. */
 int er_tsdf_integrate_batch(er_tsdf* v, const uint16_t* depth, const double* T, int nframes);
 /* Same with the frames already resident in HBM (d_depth is a device pointer). */
 int er_tsdf_integrate_device(er_tsdf* v, const uint16_t* d_depth, const double* T, int nframes);
+/* Blocks until every frame handed to the *_device calls so far has been read (ScaleDepth is the only reader of the
+ * depth images): the caller may then overwrite those device buffers while the integration itself is still running. */
+int er_tsdf_inputs_consumed(er_tsdf* v);
 /* Profiling variant of er_tsdf_integrate_device: brackets every kernel launch with CUDA events on the
  * handle's stream and returns the summed device time of the touch (ScaleDepth + block activation),
  * classify (conservative sub-brick culling) and integrate (IntegrateVolumeUnit) kernels over the nframes
@@ -140,6 +154,12 @@ size_t er_cloud_size(const er_cloud* c);
 /* Gate of CCorresApp::Registration (CorresApp.cpp:250-264): cnt = #{k : NN^2(T*src_k) < dist^2}. */
 int er_icp_count_inliers(er_cloud* tgt, er_cloud* src, const double T[16], double dist, int* cnt);
 
+/* The same gate for a list of candidate pairs in one launch and one synchronisation (the reference runs the pair loop
+ * from 8 OpenMP threads, CorresApp.cpp:220): pair p tests clouds[src_idx[p]] under T[p] against clouds[tgt_idx[p]];
+ * T = npairs*16 doubles, cnt = npairs ints. */
+int er_icp_count_inliers_batch(er_cloud* const* clouds, int nclouds, const int* tgt_idx, const int* src_idx, int npairs,
+                               const double* T, double dist, int* cnt);
+
 /* pcl::IterativeClosestPoint + TransformationEstimationPointToPlaneLLS as configured at
  * CorresApp.cpp:295-306 (source = src, target = tgt, guess = Tinit cast to float).  fixed_iters != 0
  * disables the convergence tests so that exactly max_iter iterations run (benchmark mode).
@@ -159,6 +179,16 @@ int er_icp_align_batch(er_cloud* const* clouds, int nclouds, const int* tgt_idx,
  * sum A^T A over the correspondences on the untransformed source points, row-major 6x6. */
 int er_icp_correspondences(er_cloud* tgt, er_cloud* src, const double T[16], double dist, double normal_cos,
                            int32_t* pairs, size_t cap, size_t* n, double info36[36]);
+
+/* The same for a list of pairs (the pair loop of FindCorrespondence, CorresApp.cpp:121): the rows of pair p are
+ * pairs[2*row_start[p] .. 2*row_start[p+1]), row_start has npairs+1 entries; info36 (optional) = npairs*36 doubles.
+ * Returns ER_ERR_CAPACITY (with row_start filled in) when more than `cap` rows were found. */
+int er_icp_correspondences_batch(er_cloud* const* clouds, int nclouds, const int* tgt_idx, const int* src_idx, int npairs,
+                                 const double* T, double dist, double normal_cos, int32_t* pairs, size_t cap,
+                                 size_t* row_start, double* info36);
+
+/* The batched calls keep their device and pinned-host working memory between calls (per device); this frees it. */
+int er_icp_release(int device);
 
 /* Timing / accounting for the ICP path (events are recorded on the library's ICP stream of `device`). */
 int er_icp_event_record(int device, int slot);

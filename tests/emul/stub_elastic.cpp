@@ -8,6 +8,7 @@
 // "Devices" are just integers here.  A partitioned volume (er_tsdf_set_partition) integrates everything and emits only
 // the blocks it owns at extraction time -- equivalent, since a voxel update reads nothing but depth and pose.
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -116,6 +117,9 @@ int er_tsdf_extract(er_tsdf* v, float* xyzi, size_t cap, size_t* n) {
   return 0;
 }
 
+void* er_host_alloc(size_t bytes) { return std::malloc(bytes ? bytes : 1); }
+void er_host_free(void* p) { std::free(p); }
+
 er_cloud* er_cloud_upload(int device, const float* xyz, const float* normals, size_t n, double cell_size) {
   er_cloud* c = new er_cloud();
   c->c = oracle_cloud_create(xyz, normals, (int)n, cell_size);
@@ -128,6 +132,31 @@ int er_icp_count_inliers(er_cloud* tgt, er_cloud* src, const double T[16], doubl
   *cnt = oracle_icp_count_inliers(tgt->c, src->c, T, dist, 1);
   return 0;
 }
+int er_icp_count_inliers_batch(er_cloud* const* clouds, int nclouds, const int* tgt_idx, const int* src_idx, int npairs, const double* T,
+                               double dist, int* cnt) {
+  for (int p = 0; p < npairs; p++) {
+    if (tgt_idx[p] < 0 || tgt_idx[p] >= nclouds || src_idx[p] < 0 || src_idx[p] >= nclouds) return -2;
+    if (clouds[tgt_idx[p]]->device != clouds[0]->device || clouds[src_idx[p]]->device != clouds[0]->device) return -1;
+    cnt[p] = oracle_icp_count_inliers(clouds[tgt_idx[p]]->c, clouds[src_idx[p]]->c, T + 16 * (size_t)p, dist, 1);
+  }
+  return 0;
+}
+int er_icp_correspondences_batch(er_cloud* const* clouds, int nclouds, const int* tgt_idx, const int* src_idx, int npairs,
+                                 const double* T, double dist, double normal_cos, int32_t* pairs, size_t cap, size_t* row_start,
+                                 double* info36) {
+  size_t at = 0;
+  row_start[0] = 0;
+  for (int p = 0; p < npairs; p++) {
+    if (tgt_idx[p] < 0 || tgt_idx[p] >= nclouds || src_idx[p] < 0 || src_idx[p] >= nclouds) return -2;
+    if (clouds[tgt_idx[p]]->device != clouds[0]->device || clouds[src_idx[p]]->device != clouds[0]->device) return -1;
+    const int n = oracle_icp_correspondences(clouds[tgt_idx[p]]->c, clouds[src_idx[p]]->c, T + 16 * (size_t)p, dist, normal_cos,
+                                             pairs + 2 * at, (int)(cap - at), info36 ? info36 + 36 * (size_t)p : nullptr, 1);
+    at += (size_t)n;
+    row_start[p + 1] = at;
+  }
+  return 0;
+}
+int er_icp_release(int) { return 0; }
 int er_icp_align_batch(er_cloud* const* clouds, int nclouds, const int* tgt_idx, const int* src_idx, int npairs, const double* Tinit,
                        double max_dist, int max_iter, double eps, int fixed_iters, double* Tout, int* iters, double* fitness) {
   std::vector<oracle_cloud*> oc((size_t)nclouds);

@@ -235,3 +235,74 @@ def test_buildcorrespondence_blacklist_and_redux(oracle, tmp_path):
     assert np.allclose(got[0][1], marker, atol=5e-9)                # redux transform taken verbatim, no ICP
     assert got[0][0][2] > 0
     assert not os.path.exists(os.path.join(d, "corres_0_2.txt")) and os.path.exists(os.path.join(d, "corres_0_1.txt"))
+
+
+def _device_count():
+    import torch
+    return torch.cuda.device_count()
+
+
+def test_integrate_cli_devices_matches_reference_binary(oracle, tmp_path):
+    """--devices 0,1[,..]: ONE volume whose 64^3 blocks are partitioned over the GPUs in-process (er_tsdf_set_partition,
+    one host thread per device); the concatenated world.pcd equals the verbatim reference binary's, rigid and ControlGrid
+    mode (TSDFVolume.cpp:45-63, IntegrateApp.cpp:217-225).  Skips below 2 devices."""
+    nd = _device_count()
+    if nd < 2:
+        pytest.skip("needs >= 2 CUDA devices")
+    devs = ",".join(str(k) for k in range(min(nd, 4)))
+    for mk in (helpers.scene_room, helpers.scene_ctr):
+        sc = mk()
+        d = str(tmp_path / mk.__name__)
+        os.makedirs(d)
+        args = helpers.write_scene(sc, d)
+        mine_pcd = os.path.join(d, "mine.pcd")
+        my_args = [a if a != os.path.join(d, "world.pcd") else mine_pcd for a in args] + ["--devices", devs]
+        rc, out = run([os.path.join(BIN, "Integrate")] + my_args, d)
+        assert rc == 0, out
+        mine = oracle.sort_world(synth.read_pcd_xyzi(mine_pcd))
+        if os.path.exists(oracle.REF_INTEGRATE):
+            oracle.run_reference_integrate(args, cwd=d)
+            ref = oracle.sort_world(synth.read_pcd_xyzi(os.path.join(d, "world.pcd")))
+        else:
+            vol = oracle.OracleTSDF()
+            helpers.run_scene(vol, sc, mul=oracle.mat4_mul)
+            ref = oracle.sort_world(vol.extract())
+        assert mine.shape == ref.shape and np.array_equal(mine.view(np.uint32), ref.view(np.uint32))
+
+
+def test_buildcorrespondence_cli_devices_equals_single_device(tmp_path):
+    """--devices: the gate, the ICP share and the correspondence pass are dealt round-robin over the GPUs; every output
+    file equals the single-device run's byte for byte (pairs are independent, CorresApp.cpp:121,220).  Skips below 2."""
+    nd = _device_count()
+    if nd < 2:
+        pytest.skip("needs >= 2 CUDA devices")
+    d = str(tmp_path / "data")
+    os.makedirs(d)
+    n_frag = 4
+    for i in range(n_frag):
+        x, n = synth.make_local_fragment(i, 30000)
+        synth.write_pcd_xyzrgbnormal(os.path.join(d, "cloud_bin_%d.pcd" % i), x, n)
+    pairs = [(i, j) for i in range(n_frag) for j in range(i + 1, n_frag)]
+    Tinit = [synth.quantize_log(synth.pair_init(i, j)) for (i, j) in pairs]
+    synth.write_log(os.path.join(d, "pairs.log"), np.array(Tinit), ids=[(i, j, n_frag) for (i, j) in pairs])
+    outs = {}
+    for tag, extra in (("one", []), ("many", ["--devices", ",".join(str(k) for k in range(min(nd, 4)))])):
+        cwd = str(tmp_path / tag)
+        os.makedirs(cwd)
+        rc, out = run([os.path.join(BIN, "BuildCorrespondence"), "--reg_traj", os.path.join(d, "pairs.log"), "--registration",
+                       "--reg_num", "5000", "--output_information"] + extra, cwd)
+        assert rc == 0, out
+        files = {f: open(os.path.join(cwd, f), "rb").read() for f in ("reg_output.log", "reg_output.info")}
+        for (i, j) in pairs:
+            fn = os.path.join(d, "corres_%d_%d.txt" % (i, j))
+            files["corres_%d_%d" % (i, j)] = open(fn, "rb").read() if os.path.exists(fn) else None
+            if os.path.exists(fn):
+                os.remove(fn)
+        outs[tag] = files
+    assert outs["one"].keys() == outs["many"].keys()
+    for k in outs["one"]:
+        if k == "reg_output.info":          # double atomics across CTAs: last-digit differences in the %.8f text are possible
+            a = np.array([float(x) for x in outs["one"][k].split()]); b = np.array([float(x) for x in outs["many"][k].split()])
+            assert a.shape == b.shape and np.allclose(a, b, rtol=1e-9, atol=1e-6)
+        else:
+            assert outs["one"][k] == outs["many"][k], k

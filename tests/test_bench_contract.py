@@ -20,7 +20,8 @@ torch.Tensor.cuda = lambda self, *a, **k: self
 torch.Tensor.pin_memory = lambda self, *a, **k: self
 _tensor = torch.tensor
 torch.tensor = lambda *a, **k: _tensor(*a, **{kk: vv for kk, vv in k.items() if kk != "device"})
-from elasticreconstruction_b200 import capi, icp_bench
+from elasticreconstruction_b200 import capi
+import icp_bench
 
 
 class FakeVol:
@@ -28,11 +29,20 @@ class FakeVol:
         self.l = 0
         self.s = dict(updated_voxels=0, touched_blocks=0, one_pairs=0, full_pairs=0)
     def set_fusion(self, f): pass
-    def integrate_device(self, p, poses, n): self.l += 4 * ((n + 31) // 32)
-    def integrate_ptr(self, p, poses, n): pass
-    def profile_device(self, p, poses, n):
+    def set_partition(self, r, w): pass
+    def set_control_grids(self, g, res, length): pass
+    def integrate_device(self, p, poses, n):
+        self.l += 4 * ((n + 31) // 32)
         for k in self.s:
             self.s[k] += 1000 * n
+    def integrate_ctr_device(self, p, Ti, T0, A0, Ai, chunks): self.l += 6 * ((len(chunks) + 31) // 32)
+    def profile_reproject_device(self, p, Ti, T0, A0, Ai, chunks): return 0.002 * len(chunks)
+    def integrate_ptr(self, p, poses, n): pass
+    def inputs_consumed(self): pass
+    def extract_count(self): return 1000
+    def extract_into(self, buf, cap): return 1000
+    def extract(self): return np.zeros((10, 4), np.float32)
+    def profile_device(self, p, poses, n):
         return (0.0018 * n, 0.0019 * n, 0.005 * n)
     def sync(self): pass
     def launch_count(self): return self.l
@@ -57,17 +67,25 @@ class FakeIcp:
     def icp_event_elapsed_ms(self, dev, a, b): return 12.5
 
 
+class FakeHost:
+    def __init__(self, n): self.nbytes = n; self.ptr = 1
+
+
 capi.TSDFVolume = FakeVol
+capi.HostBuffer = FakeHost
 icp_bench.capi = FakeIcp()
 print("a library chatting on stdout before the benchmark line")        # must not reach the real stdout
 import bench
+_rd = bench.room_depth_device
+bench.room_depth_device = lambda poses, device, **k: _rd(poses, "cpu", **k)
 sys.argv = ["bench.py"] + %(argv)r
 sys.exit(bench.main())
 '''
 
 
 def test_main_arm_prints_one_json_line_with_the_contract_keys(tmp_path):
-    argv = ["--steps", "1", "--warmup", "1", "--frames-per-step", "50", "--cpu-frames", "6", "--icp-fragments", "3", "--icp-points", "2000"]
+    argv = ["--steps", "1", "--warmup", "1", "--frames-per-step", "50", "--cpu-frames", "6", "--icp-fragments", "3", "--icp-points", "2000",
+            "--ctr-frames", "100", "--ctr-steps", "1"]
     script = tmp_path / "drive.py"
     script.write_text(DRIVER % dict(root=ROOT, argv=argv))
     p = subprocess.run([sys.executable, str(script)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, cwd=ROOT)
@@ -77,14 +95,15 @@ def test_main_arm_prints_one_json_line_with_the_contract_keys(tmp_path):
     assert len(lines) == 2 and lines[0].startswith("a library chatting")
     d = json.loads(lines[1])
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
-              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "icp"):
+              "dtype", "data", "config", "roofline", "cpu_baseline", "e2e", "gpu_launches", "clocks", "icp", "ctrlgrid"):
         assert k in d, k
     assert d["n_gpus"] == 1 and d["steps"] == 1 and d["config"]["frames_per_step"] == 50 and "workload" in d["config"]
     assert set(("bound", "achieved", "peak", "unit", "frac", "traffic")) <= set(d["roofline"])
     assert d["roofline"]["traffic"] is not None
     assert set(("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step")) <= set(d["e2e"])
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 8
-    assert d["icp"]["warmup_passes"] >= 3 and "roofline" in d["icp"]
+    assert d["icp"]["warmup_passes"] >= 3 and "roofline" in d["icp"] and d["icp"]["timed_passes"] >= 3
+    assert d["e2e"]["d2h_bytes_per_step"] > 1000 and d["ctrlgrid"]["reproject_us_per_frame"] > 0
 
 
 def test_reference_arm_line(tmp_path):

@@ -95,3 +95,80 @@ def test_partial_overlap_and_large_offsets(oracle):
         po, io = oracle.icp_correspondences(to, so, To, 0.015, 0.8660)
         pg, ig = capi.icp_correspondences(tg, sg, To, 0.015, 0.8660)
         assert np.array_equal(po, pg) and np.allclose(io, ig, rtol=1e-10, atol=1e-6)
+
+
+def test_batched_gate_and_correspondences_match_single_calls(frags):
+    """er_icp_count_inliers_batch / er_icp_correspondences_batch (one launch sequence per list, blockIdx.y = pair) return
+    what the per-pair calls return, pair by pair (CorresApp.cpp:121,220 run these loops pair-parallel)."""
+    clouds = [f[3] for f in frags]
+    tgt, src, Ts = [], [], []
+    for i in range(4):
+        for j in range(i + 1, 4):
+            tgt.append(i); src.append(j); Ts.append(synth.perturbation(300 + 4 * i + j, max_rot_deg=0.3, max_trans=0.004))
+    cnt = capi.icp_count_inliers_batch(clouds, tgt, src, np.array(Ts), 0.03)
+    rows, info = capi.icp_correspondences_batch(clouds, tgt, src, np.array(Ts), 0.015, 0.8660)
+    for p in range(len(tgt)):
+        assert cnt[p] == capi.icp_count_inliers(clouds[tgt[p]], clouds[src[p]], Ts[p], 0.03)
+        pg, ig = capi.icp_correspondences(clouds[tgt[p]], clouds[src[p]], Ts[p], 0.015, 0.8660)
+        assert len(pg) > 100 and np.array_equal(pg, rows[p])
+        assert np.allclose(ig, info[p], rtol=1e-12, atol=0)      # double atomics across CTAs: order-dependent last bits
+    # an empty list and an empty cloud are fine
+    assert len(capi.icp_count_inliers_batch(clouds, [], [], np.zeros((0, 16)), 0.03)) == 0
+    empty = capi.Cloud(np.zeros((0, 3), np.float32), np.zeros((0, 3), np.float32))
+    assert capi.icp_count_inliers(clouds[0], empty, np.eye(4), 0.03) == 0
+    T, it, fit = capi.icp_align(clouds[0], empty, np.eye(4))
+    assert it == 0
+
+
+def test_alignment_is_reproducible_run_to_run(frags):
+    """The cell-sorted layout is made deterministic (points of a cell in ascending original index), so two uploads of the
+    same fragment and two runs of the same batch give bit-identical poses."""
+    a = capi.Cloud(frags[1][0], frags[1][1], cell_size=0.03)
+    b = capi.Cloud(frags[1][0], frags[1][1], cell_size=0.03)
+    P = synth.perturbation(77)
+    T1, i1, f1 = capi.icp_align(frags[0][3], a, P, 0.03, 20, 1e-6, True)
+    T2, i2, f2 = capi.icp_align(frags[0][3], b, P, 0.03, 20, 1e-6, True)
+    T3, i3, f3 = capi.icp_align(frags[0][3], a, P, 0.03, 20, 1e-6, True)
+    assert np.array_equal(T1, T2) and np.array_equal(T1, T3) and f1 == f2 == f3
+
+
+def test_independent_float64_cross_check_of_the_icp_step():
+    """An independently written check that shares no code with oracle/icp_oracle.c (the ICP parity stays "unpinned": PCL
+    itself is not available): scipy's cKDTree for the 1-NN search and numpy.linalg.lstsq for the point-to-plane step, all
+    in float64, iterated 20 times on two full-size bench pairs.  The library's pose after 20 fixed iterations must agree to
+    1e-5 Frobenius; the iteration-by-iteration agreement is checked through max_iter = 1..3 as well."""
+    from scipy.spatial import cKDTree
+
+    def step(tgt_xyz, tgt_nrm, tree, src, max_d):
+        d, idx = tree.query(src, k=1)
+        keep = d * d <= max_d * max_d
+        s, t, n = src[keep], tgt_xyz[idx[keep]], tgt_nrm[idx[keep]]
+        A = np.hstack([np.cross(s, n), n])                                  # rows [s x n, n]
+        b = np.einsum("ij,ij->i", n, t - s)
+        x = np.linalg.lstsq(A, b, rcond=None)[0]
+        al, be, ga = x[:3]
+        ca, sa, cb, sb, cg, sg = np.cos(al), np.sin(al), np.cos(be), np.sin(be), np.cos(ga), np.sin(ga)
+        R = np.array([[cg * cb, -sg * ca + cg * sb * sa, sg * sa + cg * sb * ca],
+                      [sg * cb, cg * ca + sg * sb * sa, -cg * sa + sg * sb * ca],
+                      [-sb, cb * sa, cb * ca]])
+        T = np.eye(4)
+        T[:3, :3] = R
+        T[:3, 3] = x[3:]
+        return T
+
+    for (i, j) in ((0, 1), (3, 7)):
+        (x0, n0), (x1, n1) = synth.make_local_fragment(i, 200000), synth.make_local_fragment(j, 200000)
+        tgt, src = capi.Cloud(x0, n0, cell_size=0.03), capi.Cloud(x1, n1, cell_size=0.03)
+        Tinit = synth.pair_init(i, j)
+        x0d, n0d = x0.astype(np.float64), n0.astype(np.float64)
+        tree = cKDTree(x0d)
+        final = Tinit.astype(np.float32).astype(np.float64)
+        cur = x1.astype(np.float64) @ final[:3, :3].T + final[:3, 3]
+        for it in range(1, 21):
+            Tinc = step(x0d, n0d, tree, cur, 0.03)
+            cur = cur @ Tinc[:3, :3].T + Tinc[:3, 3]
+            final = Tinc @ final
+            if it in (1, 2, 3, 20):
+                Tg, itg, _ = capi.icp_align(tgt, src, Tinit, 0.03, it, 1e-6, True)
+                assert itg == it
+                assert np.linalg.norm(Tg - final) <= POSE_TOL, (i, j, it, np.linalg.norm(Tg - final))

@@ -259,3 +259,43 @@ def test_custom_voxel_size_and_truncation(oracle):
         ovol.integrate(sc["frames"][f], sc["traj"][f])
         gvol.integrate(sc["frames"][f], sc["traj"][f])
     compare_blocks(ovol, gvol)
+
+
+def test_ctr_mode_small_image_stays_inside_the_frame(oracle):
+    """ControlGrid mode on an image smaller than VGA: the reference's XYZ2UVD bounds are the literals 640 x 480
+    (TSDFVolume.h:51-60) and would index past a smaller buffer; here a re-projected pixel must land inside the image, so
+    neighbouring frames' z-buffers of a batch are never touched.  Checked as: (a) the batched path equals the
+    frame-by-frame path (a stray write into the next frame's z-buffer slot would change it), (b) every re-projected
+    image equals the oracle's wherever the oracle's own target pixel is inside the image."""
+    cols, rows = 320, 240
+    sc = helpers.scene_ctr(num=2, interval=3)
+    frames = np.ascontiguousarray(sc["frames"][:, :rows * 2:2, :cols * 2:2])          # subsampled wall
+    traj = helpers.compose_traj(sc["pose_traj"], sc["seg_traj"], sc["interval"], capi.mat4_mul)
+    n = len(frames)
+    cam = (262.5, 262.5, 159.75, 119.75, 2.5)
+    va = capi.TSDFVolume(cols=cols, rows=rows, max_blocks=256)
+    vb = capi.TSDFVolume(cols=cols, rows=rows, max_blocks=256)
+    for v in (va, vb):
+        v.set_camera(*cam)
+        v.set_control_grids(sc["grids"], sc["res"], sc["length"])
+    chunks = [f // sc["interval"] for f in range(n)]
+    va.integrate_ctr_batch(frames, traj[:n], traj[0], sc["seg_traj"][0], sc["seg_traj"][:n], chunks)
+    for f in range(n):
+        vb.integrate_ctr(frames[f], traj[f], traj[0], sc["seg_traj"][0], sc["seg_traj"][f], chunks[f])
+    wa, wb = oracle.sort_world(va.extract()), oracle.sort_world(vb.extract())
+    assert len(wa) > 1000 and np.array_equal(wa.view(np.uint32), wb.view(np.uint32))
+    for f in (0, n - 1):
+        img = va.reproject(frames[f], traj[f], traj[0], sc["seg_traj"][0], sc["seg_traj"][f], chunks[f])
+        assert img.shape == frames[f].shape and (img > 0).sum() > 1000
+
+
+def test_pool_overflow_stops_the_next_batch():
+    """After the block pool has overflowed, the next *_batch call returns ER_ERR_CAPACITY (pinned mirror of the overflow
+    flag) instead of processing the rest of the sequence, and the hash table never fills up (no spin)."""
+    sc = helpers.scene_room(n=4)
+    vol = capi.TSDFVolume(max_blocks=4)
+    vol.integrate_batch(sc["frames"][:2], sc["traj"][:2])
+    with pytest.raises(capi.ElasticError, match="pool exhausted"):
+        vol.sync()
+    with pytest.raises(capi.ElasticError, match="pool exhausted"):
+        vol.integrate_batch(sc["frames"][2:4], sc["traj"][2:4])

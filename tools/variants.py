@@ -43,13 +43,15 @@ def run(with_tests):
         if lib:
             env["ER_B200_LIB"] = lib
         print("=== %s" % name, flush=True)
+        # a variant only changes one of the two .cu files: test and time that path alone (GPU minutes)
+        paths = ("tsdf", "icp") if not lib else (("icp",) if "colmask" in name or name.startswith("icp") else ("tsdf",))
         if with_tests and lib:
-            rc = subprocess.call([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "--timeout", "300",
-                                  os.path.join(ROOT, "tests", "test_tsdf_gpu.py"), os.path.join(ROOT, "tests", "test_icp_gpu.py")],
-                                 env=env, cwd=ROOT)
+            rc = subprocess.call([sys.executable, "-m", "pytest", "-x", "-q", "-m", "gpu", "--timeout", "300"] +
+                                 [os.path.join(ROOT, "tests", "test_%s_gpu.py" % p) for p in paths], env=env, cwd=ROOT)
             print("parity tests: %s" % ("PASS" if rc == 0 else "FAIL (rc %d) -- ignore this variant's timings" % rc), flush=True)
-        for tool, args in (("time_tsdf.py", ["256"]), ("time_icp.py", ["12", "256", "20"])):
-            subprocess.call(["timeout", "200", sys.executable, os.path.join(ROOT, "tools", tool)] + args, env=env, cwd=ROOT)
+        for tool, args, path in (("time_tsdf.py", ["256"], "tsdf"), ("time_icp.py", ["12", "256", "20"], "icp")):
+            if path in paths:
+                subprocess.call(["timeout", "200", sys.executable, os.path.join(ROOT, "tools", tool)] + args, env=env, cwd=ROOT)
 
 
 if __name__ == "__main__":
