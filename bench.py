@@ -363,7 +363,7 @@ def main():
     ap.add_argument("--frames-per-step", type=int, default=SEQ_FRAMES,
                     help="frames handed to the library per call; must divide the 1000-frame sequence")
     ap.add_argument("--ref-frames-per-step", type=int, default=8)
-    ap.add_argument("--ref-pairs-per-step", type=int, default=4)
+    ap.add_argument("--ref-pairs-per-step", type=int, default=8)
     ap.add_argument("--cpu-frames", type=int, default=120, help="frames timed for cpu_baseline (0 = skip)")
     ap.add_argument("--fusion", type=int, default=32, help="frames per fused launch triple (1..32)")
     ap.add_argument("--no-icp", action="store_true")

@@ -71,7 +71,19 @@ def main():
         def to_bytes(m):
             scale = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u(m)]
             return g(m) * scale
-        traffic[name] = {"dram_bytes_per_launch": to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"),
+        def opt(m):
+            try:
+                return g(m)
+            except Exception:
+                return None
+        issue = {"issue_active_pct": opt("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                 "warp_instructions": opt("smsp__inst_executed.sum"),
+                 "sm_throughput_pct": opt("sm__throughput.avg.pct_of_peak_sustained_elapsed"),
+                 "dram_throughput_pct": opt("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+                 "active_lanes_per_instruction": opt("smsp__thread_inst_executed_per_inst_executed.ratio"),
+                 "note": "instruction issue is the binding roof of this kernel: issue_active_pct = share of cycles in which a "
+                         "scheduler issued (100 = one warp instruction per scheduler per cycle)"}
+        traffic[name] = {"issue": issue, "dram_bytes_per_launch": to_bytes("dram__bytes_read.sum") + to_bytes("dram__bytes_write.sum"),
                          "duration_us_under_ncu": g("gpu__time_duration.sum") * ({"us": 1, "ms": 1e3, "ns": 1e-3}[u("gpu__time_duration.sum")]),
                          "units_per_launch": units, "source": os.path.basename(path), "round": rnd}
     json.dump(traffic, open(traffic_path, "w"), indent=1, sort_keys=True)

@@ -23,3 +23,14 @@ vol.set_fusion(fusion)
 vol.integrate_device(d.data_ptr(), poses, n)
 vol.sync()
 print("blocks", vol.num_blocks(), "launches", vol.launch_count())
+if len(sys.argv) > 4 and sys.argv[4] == "ctr":
+    # ControlGrid mode (BASELINE configs[3] scene of bench.py) for a capture of reproject_kernel
+    import bench
+    sc = bench.ctrlgrid_scene(max(n, 100))
+    traj = np.array([capi.mat4_mul(sc["pose"][f // sc["interval"]], sc["seg"][f]) for f in range(n)])
+    dfr = bench.room_depth_device(traj, torch.device("cuda", 0), lo=0.25, hi=5.75)
+    v2 = capi.TSDFVolume(max_blocks=4096)
+    v2.set_control_grids(sc["grids"], sc["res"], sc["length"])
+    v2.integrate_ctr_device(dfr.data_ptr(), traj, traj[0], sc["seg"][0], sc["seg"][:n], (np.arange(n) // sc["interval"]).astype(np.int32))
+    v2.sync()
+    print("ctr blocks", v2.num_blocks())
