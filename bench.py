@@ -537,9 +537,10 @@ def main():
                 "dense_bytes_per_frame": 16.0 * 262144 * blocks_pf + 2.0 * W * H}
 
     # ---------------- e2e: host buffers through the C ABI, H2D inside the timed region, the voxel list back on the host
-    frames_host = d_frames.cpu()
-    pinned = frames_host.pin_memory()
-    del frames_host
+    # page-locked host frames from the library's allocator (er_host_alloc places them on the NUMA node of this rank's GPU)
+    host_frames = capi.HostBuffer(need * BYTES_PER_FRAME)
+    pinned = torch.from_numpy(host_frames.array(np.int16)).view(need, H, W)
+    pinned.copy_(d_frames)
     vol3 = new_volume(partitioned)
     cap_rows = 0
     result = None
@@ -583,9 +584,9 @@ def main():
     else:
         def e2e_step(s):
             idx = step_idx[s]
-            vol3.integrate_ptr(pinned.data_ptr() + int(idx[0]) * BYTES_PER_FRAME, poses[idx], F)
+            vol3.integrate_ptr(host_frames.ptr + int(idx[0]) * BYTES_PER_FRAME, poses[idx], F)
         h2d_per_step = F * BYTES_PER_FRAME
-        feed = "er_tsdf_integrate_batch from pinned host memory"
+        feed = "er_tsdf_integrate_batch from page-locked host memory (er_host_alloc, NUMA-local to the GPU)"
 
     for s in range(args.warmup):
         e2e_step(s)
@@ -603,7 +604,8 @@ def main():
            "d2h_bytes_per_step": int(n_rows * 16 + 8), "result_rows": int(n_rows), "feed": feed,
            "timing": "wall clock around the C-ABI calls (integrate + er_tsdf_extract of the step's voxels into pinned host "
                      "memory), barrier+sync both sides, max over ranks"}
-    del vol3, result
+    del vol3, result, pinned
+    host_frames.close()
 
     # ---------------- replica mode of round 1 (N > 1): every rank its own volume and its own frame stream
     replica = None
@@ -616,7 +618,7 @@ def main():
                    "sharding": "independent volume and frame stream per rank (round 1's mode)"}
         del rv, rframes
 
-    del d_frames, pinned
+    del d_frames
     torch.cuda.empty_cache()
 
     # ---------------- configs[3]: ControlGrid mode

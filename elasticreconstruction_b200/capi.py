@@ -66,6 +66,8 @@ SIGNATURES = {
     "er_cloud_free": (None, [C.c_void_p]),
     "er_cloud_size": (C.c_size_t, [C.c_void_p]),
     "er_icp_count_inliers": (C.c_int, [C.c_void_p, C.c_void_p, c_dp, C.c_double, c_ip]),
+    "er_cloud_get_meta": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "er_cloud_from_blob": (C.c_void_p, [C.c_int, C.c_void_p, C.c_void_p]),
     "er_icp_count_inliers_batch": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, c_ip, c_ip, C.c_int, c_dp, C.c_double, c_ip]),
     "er_icp_correspondences_batch": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, c_ip, c_ip, C.c_int, c_dp, C.c_double,
                                                C.c_double, c_i32p, C.c_size_t, c_szp, c_dp]),
@@ -388,8 +390,31 @@ class Cloud:
             raise ElasticError("er_cloud_upload failed: " + lib().er_last_error().decode("utf-8", "replace"))
         self._h = C.c_void_p(h)
 
+    META_BYTES = 8 * 7 + 8 + 4 * 5 + 4 * 4          # sizeof(er_cloud_meta) = 100, padded to 104
+
     def __len__(self):
         return int(lib().er_cloud_size(self._h))
+
+    def blob(self):
+        """(meta bytes, device pointer, blob bytes) of the built cloud (er_cloud_get_meta)."""
+        meta = (C.c_uint8 * 104)()
+        ptr = C.c_void_p()
+        _check(lib().er_cloud_get_meta(self._h, meta, C.byref(ptr)))
+        nbytes = int(np.frombuffer(bytes(meta), dtype=np.uint64, count=2)[1])
+        return bytes(meta), ptr.value, nbytes
+
+    @classmethod
+    def from_blob(cls, meta: bytes, device_ptr: int, device: int = 0):
+        """A cloud built elsewhere (er_cloud_from_blob copies the blob at device_ptr into its own allocation)."""
+        self = cls.__new__(cls)
+        self.xyz = self.normals = None
+        self.device = device
+        buf = (C.c_uint8 * 104).from_buffer_copy(meta)
+        h = lib().er_cloud_from_blob(device, buf, C.c_void_p(device_ptr))
+        if not h:
+            raise ElasticError("er_cloud_from_blob failed: " + lib().er_last_error().decode("utf-8", "replace"))
+        self._h = C.c_void_p(h)
+        return self
 
     def close(self):
         if getattr(self, "_h", None):

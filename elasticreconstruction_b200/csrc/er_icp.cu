@@ -772,6 +772,8 @@ int cuda_fail(const char* what, cudaError_t e) {
 struct er_cloud {
   int device = 0;
   size_t n = 0;
+  size_t block_bytes = 0;      // the part of d_block a copy of the cloud needs (everything but the build's scratch)
+  size_t off[5] = {};          // byte offsets of pts, nrm, xyz, nrm_orig, cell_start inside d_block
   void* d_block = nullptr;     // one allocation holding everything below
   float4* d_pts = nullptr;
   float4* d_nrm = nullptr;
@@ -828,6 +830,8 @@ er_cloud* er_cloud_upload(int device, const float* xyz, const float* normals, si
                o_no = o_xyz + up256(sizeof(float) * 3 * n), o_A = o_no + up256(sizeof(float) * 3 * n),
                o_cid = o_A + up256(sizeof(int) * (ncell + 2)), o_scan = o_cid + up256(sizeof(int) * n),
                total = o_scan + up256(scan_bytes) + 256;
+  c->off[0] = o_pts; c->off[1] = o_nrm; c->off[2] = o_xyz; c->off[3] = o_no; c->off[4] = o_A;
+  c->block_bytes = o_cid;
   if (e == cudaSuccess) e = cudaMalloc(&c->d_block, total);
   if (e == cudaSuccess) {
     char* base = (char*)c->d_block;
@@ -871,6 +875,52 @@ void er_cloud_free(er_cloud* c) {
 }
 
 size_t er_cloud_size(const er_cloud* c) { return c ? c->n : 0; }
+
+// ---- a built cloud as a self-contained blob: lets one rank build a fragment's grid and the others receive it over
+// NVLink (NCCL broadcast / all-gather of the blob) instead of every rank uploading and sorting every fragment
+int er_cloud_get_meta(const er_cloud* c, er_cloud_meta* m, const void** d_blob) {
+  ER_ARG(c && m, "cloud_get_meta: null argument");
+  std::memset(m, 0, sizeof *m);
+  m->n = c->n;
+  m->blob_bytes = c->block_bytes;
+  for (int i = 0; i < 5; i++) m->offset[i] = c->off[i];
+  m->cell = c->cell;
+  for (int a = 0; a < 3; a++) { m->org[a] = c->grid.org[a]; m->dim[a] = c->grid.dim[a]; }
+  m->inv_cell = c->grid.inv_cell;
+  m->cell_f = c->grid.cell;
+  m->rings = c->grid.rings;
+  if (d_blob) *d_blob = c->d_block;
+  return ER_OK;
+}
+
+er_cloud* er_cloud_from_blob(int device, const er_cloud_meta* m, const void* d_blob) {
+  if (!m || !d_blob || m->blob_bytes == 0) { er::set_error("er_cloud_from_blob: bad arguments"); return nullptr; }
+  if (!get_ctx(device)) { er::set_error("er_cloud_from_blob: cannot create a stream on device %d", device); return nullptr; }
+  er_cloud* c = new (std::nothrow) er_cloud();
+  if (!c) return nullptr;
+  c->device = device;
+  c->n = (size_t)m->n;
+  c->block_bytes = (size_t)m->blob_bytes;
+  for (int i = 0; i < 5; i++) c->off[i] = (size_t)m->offset[i];
+  c->cell = m->cell;
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaMalloc(&c->d_block, c->block_bytes);
+  if (e == cudaSuccess) e = cudaMemcpy(c->d_block, d_blob, c->block_bytes, cudaMemcpyDeviceToDevice);
+  if (e != cudaSuccess) {
+    er::set_error("er_cloud_from_blob: %s", cudaGetErrorString(e));
+    er_cloud_free(c);
+    return nullptr;
+  }
+  char* base = (char*)c->d_block;
+  c->d_pts = (float4*)(base + c->off[0]); c->d_nrm = (float4*)(base + c->off[1]);
+  c->d_xyz = (float*)(base + c->off[2]); c->d_nrm_orig = (float*)(base + c->off[3]);
+  c->d_cell_start = (int*)(base + c->off[4]);
+  GridDev& g = c->grid;
+  g.pts = c->d_pts; g.nrm = c->d_nrm; g.cell_start = c->d_cell_start; g.xyz_orig = c->d_xyz; g.nrm_orig = c->d_nrm_orig;
+  for (int a = 0; a < 3; a++) { g.org[a] = m->org[a]; g.dim[a] = m->dim[a]; }
+  g.inv_cell = m->inv_cell; g.cell = m->cell_f; g.rings = m->rings;
+  return c;
+}
 
 int er_icp_release(int device) {
   IcpCtx* ctx = get_ctx(device);

@@ -25,6 +25,13 @@ TIMED_PASSES = 5
 REG_DIST = 0.03
 
 
+class _DevicePtr:
+    """A raw device pointer as a __cuda_array_interface__ object (zero-copy torch.as_tensor)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
 def all_pairs(n):
     return [(i, j) for i in range(n) for j in range(i + 1, n)]
 
@@ -127,14 +134,44 @@ def run(local: int, rank: int, world: int, barrier, peak_gbs: float = 0.0, cpu_p
     # ---- e2e: host buffers -> upload (H2D + grid build) -> align -> poses back on the host
     barrier()
     t0 = time.perf_counter()
-    # fragments are uploaded from 8 host threads, like the reference loads them (omp parallel for, CorresApp.cpp:82)
+    # fragments are uploaded from 8 host threads, like the reference loads them (omp parallel for, CorresApp.cpp:82).
+    # N > 1: rank r uploads and grid-builds only the fragments i % N == r; the built clouds (sorted points + cell table,
+    # ~43 MB each) then travel to the other ranks over NVLink (NCCL broadcast) -- every rank needs every fragment, but no
+    # fragment is sorted twice and the H2D traffic is split over the ranks' PCIe links
     from concurrent.futures import ThreadPoolExecutor
+    own = [i for i in range(num_fragments) if i % world == rank]
     with ThreadPoolExecutor(max_workers=8) as ex:
-        clouds = list(ex.map(lambda xn: capi.Cloud(xn[0], xn[1], device=local, cell_size=REG_DIST), frags))
+        built = dict(zip(own, ex.map(lambda i: capi.Cloud(frags[i][0], frags[i][1], device=local, cell_size=REG_DIST), own)))
+    if world > 1:
+        dev = torch.device("cuda", local)
+        metas = torch.zeros((num_fragments, 104), dtype=torch.uint8, device=dev)
+        blobs = {}
+        for i, c in built.items():
+            meta, ptr, nbytes = c.blob()
+            metas[i] = torch.frombuffer(bytearray(meta), dtype=torch.uint8).to(dev)
+            blobs[i] = (ptr, nbytes)
+        dist.all_reduce(metas, op=dist.ReduceOp.SUM)          # every row is non-zero on exactly one rank
+        metas_h = metas.cpu().numpy()
+        clouds = []
+        for i in range(num_fragments):
+            nbytes = int(metas_h[i].view(np.uint64)[1])
+            if i in built:
+                buf = torch.as_tensor(_DevicePtr(blobs[i][0], nbytes), device=dev)    # zero-copy view of the cloud's blob
+            else:
+                buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            dist.broadcast(buf, src=i % world)
+            if i in built:
+                clouds.append(built[i])
+            else:
+                torch.cuda.current_stream().synchronize()
+                clouds.append(capi.Cloud.from_blob(metas_h[i].tobytes(), buf.data_ptr(), device=local))
+                del buf
+    else:
+        clouds = [built[i] for i in range(num_fragments)]
     T, its, fit = capi.icp_align_batch(clouds, tgt, src, Tinit, REG_DIST, ITERS, 1e-6, True)
     barrier()
     e2e_s = time.perf_counter() - t0
-    h2d = sum(x.nbytes + n.nbytes for (x, n) in frags)              # xyz + normals once; the sort happens on the device
+    h2d = sum(frags[i][0].nbytes + frags[i][1].nbytes for i in own)  # xyz + normals of this rank's share; sorted on the device
 
     # ---- value: fragments resident; three untimed passes over the whole share (W >= 3: the first one after the host
     # phases above runs while the SM clock is still ramping up), then the whole share once more, device-timed
@@ -186,8 +223,8 @@ def run(local: int, rank: int, world: int, barrier, peak_gbs: float = 0.0, cpu_p
         "passes_max_over_min": float(max(passes) / min(passes)), "clocks": clocks,
         "e2e": {"value": total_iters / (float(t[1].item()) * 1e-3), "unit": "pair-iterations/s",
                 "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(len(mine) * 136),
-                "note": "first call in the process: includes the upload of all %d fragments (H2D + device-side grid "
-                        "build), the alignment and the poses coming back" % num_fragments},
+                "note": "first call in the process: includes the upload of this rank's share of the %d fragments (H2D + device-side "
+                        "grid build), their exchange between the ranks, the alignment and the poses coming back" % num_fragments},
         "roofline": {"bound": "hbm", "kernel": "icp_iter_kernel", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s",
                      "frac": (achieved / peak_gbs) if peak_gbs else None, "traffic": _traffic_per_pair_iteration(),
                      "algorithmic_bytes_per_pair_iteration": alg_bytes,

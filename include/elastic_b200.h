@@ -50,7 +50,8 @@ void er_mat4_mul(const double a[16], const double b[16], double out[16]);
 void er_mat4_inverse(const double m[16], double out[16]);      /* Matrix4d::inverse(), TSDFVolume.cpp:40 */
 
 /* Page-locked host memory for frame buffers handed to the *_batch calls: host->device copies from pageable memory are
- * staged by the driver at a fraction of the link rate.  (The reference keeps frames in std::vector, IntegrateApp.h.) */
+ * staged by the driver at a fraction of the link rate.  The pages are placed on the NUMA node of the calling thread's
+ * current CUDA device (cudaSetDevice first).  (The reference keeps frames in std::vector, IntegrateApp.h.) */
 void* er_host_alloc(size_t bytes);
 void er_host_free(void* p);
 
@@ -150,6 +151,18 @@ typedef struct er_icp er_icp;
 er_cloud* er_cloud_upload(int device, const float* xyz, const float* normals, size_t n, double cell_size);
 void er_cloud_free(er_cloud* c);
 size_t er_cloud_size(const er_cloud* c);
+
+/* A built cloud as a self-contained device blob (sorted points, normals, original-order copies, cell table): one rank
+ * builds a fragment, the others receive meta + blob (NCCL over NVLink) and call er_cloud_from_blob, which copies the blob
+ * into an allocation of its own.  d_blob is a device pointer valid while the cloud lives. */
+typedef struct er_cloud_meta {
+  uint64_t n, blob_bytes, offset[5];
+  double cell;
+  float org[3], inv_cell, cell_f;
+  int32_t rings, dim[3];
+} er_cloud_meta;
+int er_cloud_get_meta(const er_cloud* c, er_cloud_meta* meta, const void** d_blob);
+er_cloud* er_cloud_from_blob(int device, const er_cloud_meta* meta, const void* d_blob);
 
 /* Gate of CCorresApp::Registration (CorresApp.cpp:250-264): cnt = #{k : NN^2(T*src_k) < dist^2}. */
 int er_icp_count_inliers(er_cloud* tgt, er_cloud* src, const double T[16], double dist, int* cnt);

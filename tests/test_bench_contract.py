@@ -68,7 +68,12 @@ class FakeIcp:
 
 
 class FakeHost:
-    def __init__(self, n): self.nbytes = n; self.ptr = 1
+    def __init__(self, n):
+        self.nbytes = n
+        self._a = np.zeros(n, dtype=np.uint8)
+        self.ptr = self._a.ctypes.data
+    def array(self, dtype, count=None): return self._a.view(dtype)
+    def close(self): pass
 
 
 capi.TSDFVolume = FakeVol

@@ -172,3 +172,20 @@ def test_independent_float64_cross_check_of_the_icp_step():
                 Tg, itg, _ = capi.icp_align(tgt, src, Tinit, 0.03, it, 1e-6, True)
                 assert itg == it
                 assert np.linalg.norm(Tg - final) <= POSE_TOL, (i, j, it, np.linalg.norm(Tg - final))
+
+
+def test_cloud_blob_roundtrip(frags):
+    """er_cloud_get_meta / er_cloud_from_blob: a cloud rebuilt from another cloud's device blob (how the ranks exchange built
+    fragments over NVLink) behaves exactly like the original in both roles."""
+    a = frags[1][3]
+    meta, ptr, nbytes = a.blob()
+    assert nbytes > len(a) * 56
+    b = capi.Cloud.from_blob(meta, ptr, device=0)
+    assert len(b) == len(a)
+    P = synth.perturbation(55)
+    for tgt, src in ((frags[0][3], b), (b, frags[0][3])):
+        ref_t, ref_s = (frags[0][3], a) if src is b else (a, frags[0][3])
+        T1, i1, f1 = capi.icp_align(ref_t, ref_s, P, 0.03, 20, 1e-6, True)
+        T2, i2, f2 = capi.icp_align(tgt, src, P, 0.03, 20, 1e-6, True)
+        assert i1 == i2 and np.array_equal(T1, T2) and f1 == f2
+        assert capi.icp_count_inliers(ref_t, ref_s, P, 0.03) == capi.icp_count_inliers(tgt, src, P, 0.03)
