@@ -56,19 +56,10 @@ constexpr int kMaxItems = 32 * ((2 * kMaxRings + 1) * (2 * kMaxRings + 1) + 1);
 constexpr int kRunCap = 64;            // per-warp list of point runs waiting to be scanned (drained at 32)
 constexpr int kNoMatch = 0x7fffffff;
 
-// The working copy of a pair's source points is streamed (read once, written once per iteration, 2.4 MB each way per
-// pair): -DER_ICP_CUR_STREAM=1 marks those accesses evict-first so that they do not push the target grids, which
-// every query gathers from, out of L2.
-#ifndef ER_ICP_CUR_STREAM
-#define ER_ICP_CUR_STREAM 1
-#endif
-#if ER_ICP_CUR_STREAM
-#define ER_LDCUR(p) __ldcs(p)
-#define ER_STCUR(p, v) __stcs((p), (v))
-#else
+// (evict-first hints on the streamed working copy of the source points were measured in round 2: 381.9 vs 382.1 ms per
+// 1225-pair pass -- no effect, not kept)
 #define ER_LDCUR(p) (*(p))
 #define ER_STCUR(p, v) (*(p) = (v))
-#endif
 
 struct PairState {
   GridDev tgt;
@@ -292,26 +283,6 @@ __global__ void __launch_bounds__(kThreads, MINB * 128 / kThreads) icp_iter_kern
       }
       total = 2 * __popc(bal);
     }
-#ifdef ER_ICP_COLMASK
-    // (option, not yet measured) one ballot round per column that some lane of the warp actually wants: the lane's
-    // rectangle of offsets as a 25-bit mask over kColumnOrder, OR-ed over the warp
-    unsigned want = 0;
-    if (valid) {
-      constexpr unsigned X0 = kColMaskX[2], X1 = kColMaskX[3], X2 = kColMaskX[4], Xm1 = kColMaskX[1], Xm2 = kColMaskX[0];
-      constexpr unsigned Y0 = kColMaskY[2], Y1 = kColMaskY[3], Y2 = kColMaskY[4], Ym1 = kColMaskY[1], Ym2 = kColMaskY[0];
-      const unsigned mx = X0 | (xhi >= 1 ? X1 : 0u) | (xhi >= 2 ? X2 : 0u) | (xlo <= -1 ? Xm1 : 0u) | (xlo <= -2 ? Xm2 : 0u);
-      const unsigned my = Y0 | (yhi >= 1 ? Y1 : 0u) | (yhi >= 2 ? Y2 : 0u) | (ylo <= -1 ? Ym1 : 0u) | (ylo <= -2 ? Ym2 : 0u);
-      want = mx & my & ~1u;                                       // column 0 was listed above
-    }
-    for (unsigned m = __reduce_or_sync(0xffffffffu, want); m; m &= m - 1) {
-      const int t = __ffs(m) - 1;
-      const int ox = kColumnOrder[t][0], oy = kColumnOrder[t][1];
-      const bool in = (want >> t) & 1u;
-      const unsigned bal = __ballot_sync(0xffffffffu, in);
-      if (in) s_items[warp][total + __popc(bal & lt_mask)] = (unsigned short)(lane | ((ox + 8) << 5) | ((oy + 8) << 9));
-      total += __popc(bal);
-    }
-#else
     const int reach = __reduce_max_sync(0xffffffffu, max(max(-xlo, xhi), max(-ylo, yhi)));   // 0 for idle lanes
     const int ncol = reach == 0 ? 1 : (reach == 1 ? 9 : 25);
     for (int t = 1; t < ncol; t++) {
@@ -321,7 +292,6 @@ __global__ void __launch_bounds__(kThreads, MINB * 128 / kThreads) icp_iter_kern
       if (in) s_items[warp][total + __popc(bal & lt_mask)] = (unsigned short)(lane | ((ox + 8) << 5) | ((oy + 8) << 9));
       total += __popc(bal);
     }
-#endif
     __syncwarp();
     // The items are dealt round-robin to the lanes whatever query they belong to.  First every lane derives its
     // column's run of z cells from the freshest bound of the owning query (most items end here) and the surviving

@@ -27,23 +27,6 @@ signed char kColumnOrder[25][2] = {
     {0, 0},  {-1, 0}, {1, 0},  {0, -1}, {0, 1},  {-1, -1}, {-1, 1}, {1, -1}, {1, 1},  {-2, 0}, {2, 0},  {0, -2}, {0, 2},
     {-2, -1}, {-2, 1}, {2, -1}, {2, 1}, {-1, -2}, {-1, 2}, {1, -2}, {1, 2},  {-2, -2}, {-2, 2}, {2, -2}, {2, 2}};
 
-// bit t of the result: column t of kColumnOrder has x (resp. y) offset o  (compile-time constants)
-constexpr int kColX[25] = {0, -1, 1, 0, 0, -1, -1, 1, 1, -2, 2, 0, 0, -2, -2, 2, 2, -1, -1, 1, 1, -2, -2, 2, 2};
-constexpr int kColY[25] = {0, 0, 0, -1, 1, -1, 1, -1, 1, 0, 0, -2, 2, -1, 1, -1, 1, -2, 2, -2, 2, -2, 2, -2, 2};
-constexpr unsigned col_mask_of(const int* a, int o) {
-  unsigned m = 0;
-  for (int t = 0; t < 25; t++)
-    if (a[t] == o) m |= 1u << t;
-  return m;
-}
-// (constants, not calls: device code may not call a host constexpr function)
-constexpr unsigned kColMaskX[5] = {col_mask_of(kColX, -2), col_mask_of(kColX, -1), col_mask_of(kColX, 0), col_mask_of(kColX, 1),
-                                   col_mask_of(kColX, 2)};
-constexpr unsigned kColMaskY[5] = {col_mask_of(kColY, -2), col_mask_of(kColY, -1), col_mask_of(kColY, 0), col_mask_of(kColY, 1),
-                                   col_mask_of(kColY, 2)};
-static_assert((kColMaskX[0] | kColMaskX[1] | kColMaskX[2] | kColMaskX[3] | kColMaskX[4]) == 0x1ffffffu, "kColX covers the table");
-static_assert((kColMaskX[2] & kColMaskY[2]) == 1u, "column 0 is the query's own");
-
 struct GridDev {
   const er_float4* pts;      // sorted by cell: x, y, z, original index (int bits)
   const er_float4* nrm;      // same order
