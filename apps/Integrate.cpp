@@ -16,6 +16,7 @@
 #include <cstdio>
 #include <iostream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "elastic_b200.h"
@@ -142,14 +143,23 @@ struct App {
     if (!bufs[0] || !bufs[1]) return fail("er_host_alloc");
     std::vector<double> poses(16 * chunk_frames), segs(16 * chunk_frames);
     std::vector<int> chunks(chunk_frames);
+    // the next chunk is read by a helper thread while this one is gated, copied and enqueued
     int which = 0;
+    int got_next = 0;
+    double rd_ms = 0;
+    auto read_into = [&](uint16_t* b) {
+      const auto tr0 = std::chrono::steady_clock::now();
+      got_next = src.read(b, chunk_frames);
+      rd_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count();
+    };
+    read_into(bufs[0]);
     while (!exit_) {
       uint16_t* buf = bufs[which];
-      which ^= 1;
-      const auto tr0 = std::chrono::steady_clock::now();
-      const int got = src.read(buf, chunk_frames);
-      read_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tr0).count();
+      const int got = got_next;
       if (got == 0) break;                                    // end of stream
+      which ^= 1;
+      std::thread reader(read_into, bufs[which]);
+      struct Join { std::thread& t; ~Join() { if (t.joinable()) t.join(); } } join_reader{reader};
       int nb = 0;
       for (int i = 0; i < got && !exit_; i++) {
         frame_id++;                                           // FrameID is 1-based (IntegrateApp.cpp:185)
@@ -186,6 +196,7 @@ struct App {
           }
       }
     }
+    read_ms = rd_ms;
     for (er_tsdf* vol : vols)
       if (er_tsdf_sync(vol)) return fail("er_tsdf_sync");
     return true;

@@ -3,6 +3,8 @@
 // Every reader/writer states the reference code whose behaviour it reproduces (paths relative to the
 // reference checkout).  Header-only, host C++17, no third-party dependencies (the reference used PCL/Boost).
 #pragma once
+#include <fcntl.h>
+#include <unistd.h>
 
 #include <cmath>
 #include <cstdint>
@@ -158,27 +160,40 @@ inline bool load_ctr(const std::string& filename, int num, int res, std::vector<
 // OpenNI is not available here, so "-oni <file>" names a raw container instead: little-endian int32 n, w, h
 // followed by n*w*h uint16 millimetres (0 = invalid); FrameID = 1, 2, ... (IntegrateApp.cpp:185).
 struct DepthStream {
-  FILE* f = nullptr;
+  int fd = -1;
   int n = 0, w = 0, h = 0, next = 0;
   bool open(const std::string& filename) {
-    f = std::fopen(filename.c_str(), "rb");
-    if (!f) return false;
+    fd = ::open(filename.c_str(), O_RDONLY);
+    if (fd < 0) return false;
     int32_t hdr[3];
-    if (std::fread(hdr, sizeof(int32_t), 3, f) != 3 || hdr[0] < 0 || hdr[1] <= 0 || hdr[2] <= 0) { std::fclose(f); f = nullptr; return false; }
+    if (::pread(fd, hdr, sizeof hdr, 0) != (ssize_t)sizeof hdr || hdr[0] < 0 || hdr[1] <= 0 || hdr[2] <= 0) { ::close(fd); fd = -1; return false; }
     n = hdr[0]; w = hdr[1]; h = hdr[2];
     return true;
   }
-  // reads up to `count` frames; returns how many were read
+  // reads up to `count` frames; returns how many were read.  The frames of one call are fetched by four threads with
+  // pread (the page cache delivers ~7 GB/s per thread; a 32-frame chunk is 20 MB)
   int read(uint16_t* dst, int count) {
-    if (!f) return 0;
-    int got = 0;
-    while (got < count && next < n) {
-      if (std::fread(dst + (size_t)got * w * h, sizeof(uint16_t), (size_t)w * h, f) != (size_t)w * h) { next = n; break; }
-      got++; next++;
+    if (fd < 0) return 0;
+    const int want = std::min(count, n - next);
+    if (want <= 0) return 0;
+    const size_t fb = sizeof(uint16_t) * (size_t)w * h;
+    int ok = want;
+#pragma omp parallel for num_threads(4) schedule(static) reduction(min : ok)
+    for (int i = 0; i < want; i++) {
+      size_t got = 0;
+      const off_t off = (off_t)(12 + fb * (size_t)(next + i));
+      while (got < fb) {
+        const ssize_t r = ::pread(fd, (char*)dst + fb * (size_t)i + got, fb - got, off + (off_t)got);
+        if (r <= 0) break;
+        got += (size_t)r;
+      }
+      if (got != fb) ok = std::min(ok, i);                // a short file: frames before the first short one count
     }
-    return got;
+    if (ok < want) { next = n; return ok; }
+    next += want;
+    return want;
   }
-  ~DepthStream() { if (f) std::fclose(f); }
+  ~DepthStream() { if (fd >= 0) ::close(fd); }
 };
 
 // world.pcd: pcl::io::savePCDFile(filename, PointCloud<PointXYZI>, binary=true) (Integrate/TSDFVolume.cpp:130).

@@ -374,7 +374,7 @@ def main():
     ap.add_argument("--ctr-frames", type=int, default=1000)
     ap.add_argument("--ctr-steps", type=int, default=3)
     ap.add_argument("--ctr-pool", type=int, default=4096)
-    ap.add_argument("--e2e-chunk", type=int, default=125, help="frames per H2D/all-gather chunk of the sharded feed (N > 1)")
+    ap.add_argument("--e2e-chunk", type=int, default=200, help="frames per H2D/all-gather chunk of the sharded feed (N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -549,8 +549,8 @@ def main():
         # sharded feed: rank r copies its 1/N slice of every chunk over its own PCIe link, the ranks all-gather the chunk
         # over NVLink (NCCL), the library integrates it from HBM; two chunk buffers so that the copy/gather of chunk c + 1
         # runs while chunk c is integrated
-        C = args.e2e_chunk
-        assert F % C == 0 and C % world == 0, "--e2e-chunk must divide --frames-per-step and be a multiple of the rank count"
+        C = next((c for c in range(min(args.e2e_chunk, F), 0, -1) if F % c == 0 and c % world == 0), None)
+        assert C, "--frames-per-step must be a multiple of the rank count"
         per = C // world
         gath = [torch.empty((C, H, W), dtype=torch.int16, device=dev) for _ in range(2)]
         mine = [torch.empty((per, H, W), dtype=torch.int16, device=dev) for _ in range(2)]
@@ -566,7 +566,7 @@ def main():
                 with torch.cuda.stream(feed_stream):
                     lo = f0 + c * C + rank * per
                     mine[b].copy_(pinned[lo:lo + per], non_blocking=True)
-                    dist.all_gather_into_tensor(gath[b], mine[b])
+                    dist.all_gather_into_tensor(gath[b].view(torch.uint8), mine[b].view(torch.uint8))   # (NCCL has no int16)
                     evs[b] = torch.cuda.Event()
                     evs[b].record(feed_stream)
 

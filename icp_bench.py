@@ -132,6 +132,12 @@ def run(local: int, rank: int, world: int, barrier, peak_gbs: float = 0.0, cpu_p
     src = [p[1] for p in mine]
 
     # ---- e2e: host buffers -> upload (H2D + grid build) -> align -> poses back on the host
+    if world > 1:
+        # the first broadcast / uint8 all-reduce of a process sets up NCCL channels (hundreds of ms): not part of the workload
+        wdev = torch.device("cuda", local)
+        for src_rank in range(world):
+            dist.broadcast(torch.zeros(1 << 20, dtype=torch.uint8, device=wdev), src=src_rank)
+        dist.all_reduce(torch.zeros(128, dtype=torch.uint8, device=wdev), op=dist.ReduceOp.SUM)
     barrier()
     t0 = time.perf_counter()
     # fragments are uploaded from 8 host threads, like the reference loads them (omp parallel for, CorresApp.cpp:82).

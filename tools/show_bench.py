@@ -1,0 +1,19 @@
+"""Print the key figures of a bench.py JSON line (file argument)."""
+import json
+import sys
+
+d = json.loads(open(sys.argv[1]).read().strip().splitlines()[-1])
+r = d["roofline"]
+print("N=%d value %.0f frames/s (%s) e2e %.0f frac %.3f" % (d["n_gpus"], d["value"], d["scaling"], d["e2e"]["value"], r["frac"]))
+print("  touch %.2f classify %.2f integrate %.2f serial %.2f pipelined %.2f us/frame" % (
+    r["touch_us_per_frame"], r["classify_us_per_frame"], r["integrate_us_per_frame"], r["serial_us_per_frame"], r["pipelined_us_per_frame"]))
+print("  e2e feed:", d["e2e"].get("feed"), "rows", d["e2e"].get("result_rows"))
+print("  union:", d.get("union_check"))
+print("  replica:", d.get("replica"))
+if d.get("ctrlgrid"):
+    c = d["ctrlgrid"]
+    print("  ctrlgrid %.0f frames/s, reproject %.2f us/frame, blocks %d" % (c["value"], c["reproject_us_per_frame"], c["allocated_blocks"]))
+if d.get("icp"):
+    i = d["icp"]
+    print("  icp %.0f pair-it/s passes %s e2e %.0f cpu %s" % (i["value"], i["passes_ms"], i["e2e"]["value"], (i.get("cpu_baseline") or {}).get("value")))
+print("  cpu_baseline:", (d.get("cpu_baseline") or {}).get("value"), "clocks", d.get("clocks"))
