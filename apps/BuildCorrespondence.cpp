@@ -93,11 +93,11 @@ struct CorresApp {
 
   // "<target index> <source index>" per line (CorresApp.cpp:175-184), formatted by hand into one buffer: fprintf per
   // line dominates the run time of the correspondence pass otherwise
-  static void write_corres_file(const char* fn, const std::vector<int32_t>& rows) {
+  static void write_corres_file(const char* fn, const int32_t* rows, size_t nrows) {
     FILE* f = std::fopen(fn, "w");
     if (!f) return;
     std::string buf;
-    buf.reserve(rows.size() * 8 + 16);
+    buf.reserve(nrows * 16 + 16);
     char tmp[32];
     auto put = [&](int v) {
       int n = 0;
@@ -106,7 +106,7 @@ struct CorresApp {
       if (v < 0) buf.push_back('-');
       while (n) buf.push_back(tmp[--n]);
     };
-    for (size_t k = 0; k + 1 < rows.size(); k += 2) { put(rows[k]); buf.push_back(' '); put(rows[k + 1]); buf.push_back('\n'); }
+    for (size_t k = 0; k < 2 * nrows; k += 2) { put(rows[k]); buf.push_back(' '); put(rows[k + 1]); buf.push_back('\n'); }
     std::fwrite(buf.data(), 1, buf.size(), f);
     std::fclose(f);
   }
@@ -413,8 +413,12 @@ struct CorresApp {
       const FramedTransformation& d = corres_traj.data[i];
       if (!blacklisted(d) && d.frame != -1) cand.push_back(i);              // -1 means reject
     }
-    const size_t kBatchRows = 24u << 20;                                    // rows (source points) per batch: 192 MB of pairs
+    const size_t kBatchRows = 24u << 20;                                    // rows (source points) per device and batch: 192 MB of pairs
     const int ndev = 1 + (int)extra_devices.size();
+    // one page-locked result buffer per device, reused by every batch; the corres files are written straight from it
+    std::vector<int32_t*> dev_buf((size_t)ndev, nullptr);
+    std::vector<size_t> dev_cap((size_t)ndev, 0);
+    struct FreeBufs { std::vector<int32_t*>& b; ~FreeBufs() { for (auto* p : b) er_host_free(p); } } free_bufs{dev_buf};
     for (size_t c0 = 0; c0 < cand.size();) {
       size_t c1 = c0, rows = 0;
       while (c1 < cand.size() && (c1 == c0 || rows + pointclouds[corres_traj.data[cand[c1]].id2].size() <= kBatchRows * (size_t)ndev)) {
@@ -424,7 +428,8 @@ struct CorresApp {
       const int nb = (int)(c1 - c0);
       std::vector<int> ti(nb), si(nb);
       std::vector<double> Tc(16 * (size_t)nb), info(output_information ? 36 * (size_t)nb : 0);
-      std::vector<std::vector<int32_t>> rows_of((size_t)nb);
+      std::vector<const int32_t*> rows_ptr((size_t)nb, nullptr);
+      std::vector<size_t> rows_n((size_t)nb, 0);
       for (int p = 0; p < nb; p++) {
         const FramedTransformation& d = corres_traj.data[cand[c0 + p]];
         ti[p] = d.id1; si[p] = d.id2;
@@ -432,7 +437,7 @@ struct CorresApp {
       }
       const auto tc0 = std::chrono::steady_clock::now();
       std::string err;
-      if (!on_devices(nb, [&](int, const std::vector<int>& sel, er_cloud* const* cl, std::string& e) {
+      if (!on_devices(nb, [&](int k, const std::vector<int>& sel, er_cloud* const* cl, std::string& e) {
             const int m = (int)sel.size();
             std::vector<int> t2(m), s2(m);
             std::vector<double> T2(16 * (size_t)m), I2(output_information ? 36 * (size_t)m : 0);
@@ -442,12 +447,21 @@ struct CorresApp {
               std::memcpy(&T2[16 * (size_t)q], &Tc[16 * (size_t)sel[q]], 16 * sizeof(double));
               cap += pointclouds[si[sel[q]]].size();
             }
-            std::vector<int32_t> buf(2 * (cap ? cap : 1));
+            // (a single pair larger than the batch size gets a buffer of its own size)
+            const size_t want = std::max(cap, (size_t)1);
+            if (!dev_buf[(size_t)k] || want > dev_cap[(size_t)k]) {
+              er_host_free(dev_buf[(size_t)k]);
+              dev_cap[(size_t)k] = std::max(want, kBatchRows);
+              dev_buf[(size_t)k] = (int32_t*)er_host_alloc(sizeof(int32_t) * 2 * dev_cap[(size_t)k]);
+              if (!dev_buf[(size_t)k]) { e = er_last_error(); dev_cap[(size_t)k] = 0; return; }
+            }
+            int32_t* buf = dev_buf[(size_t)k];
             std::vector<size_t> start((size_t)m + 1);
-            if (er_icp_correspondences_batch(cl, num, t2.data(), s2.data(), m, T2.data(), dist_thresh, normal_thresh, buf.data(), cap,
+            if (er_icp_correspondences_batch(cl, num, t2.data(), s2.data(), m, T2.data(), dist_thresh, normal_thresh, buf, cap,
                                              start.data(), output_information ? I2.data() : nullptr)) { e = er_last_error(); return; }
             for (int q = 0; q < m; q++) {
-              rows_of[(size_t)sel[q]].assign(buf.begin() + 2 * start[q], buf.begin() + 2 * start[q + 1]);
+              rows_ptr[(size_t)sel[q]] = buf + 2 * start[q];
+              rows_n[(size_t)sel[q]] = start[q + 1] - start[q];
               if (output_information) std::memcpy(&info[36 * (size_t)sel[q]], &I2[36 * (size_t)q], 36 * sizeof(double));
             }
           }, err)) {
@@ -458,7 +472,7 @@ struct CorresApp {
       for (int p = 0; p < nb; p++) {
         const int i = cand[c0 + p];
         FramedTransformation& d = corres_traj.data[i];
-        const size_t n = rows_of[(size_t)p].size() / 2;
+        const size_t n = rows_n[(size_t)p];
         std::printf("Processing pair <%d, %d>\n", d.id1, d.id2);
         std::printf("    <%d, %d> : Corresponce number is %d, ratio is %.2f(%d)\n", d.id1, d.id2, (int)n, (double)n / (double)d.frame, d.frame);
         if ((double)n / (double)d.frame < 0.5) {
@@ -479,7 +493,7 @@ struct CorresApp {
           const FramedTransformation& d = corres_traj.data[cand[c0 + p]];
           char fn[1024];
           std::snprintf(fn, sizeof fn, "%scorres_%d_%d.txt", dir_name.c_str(), d.id1, d.id2);
-          write_corres_file(fn, rows_of[(size_t)p]);
+          write_corres_file(fn, rows_ptr[(size_t)p], rows_n[(size_t)p]);
         }
         write_ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - tw0).count();
       }
