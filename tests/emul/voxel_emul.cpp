@@ -124,6 +124,20 @@ static void build_level(const float* scaled, int cols, int rows, int ntx, int nt
 static int g_explore = 0;
 void emul_set_explore(int mode) { g_explore = mode; }
 
+// scale_depth_div1000 against the division for every float in [lo, hi): number of mismatches
+long long emul_check_div1000(float lo, float hi) {
+  unsigned a, b;
+  std::memcpy(&a, &lo, 4);
+  std::memcpy(&b, &hi, 4);
+  long long bad = 0;
+  for (unsigned u = a; u < b; u++) {
+    float x;
+    std::memcpy(&x, &u, 4);
+    if (scale_depth_div1000(x) != x / 1000.0f) bad++;
+  }
+  return bad;
+}
+
 static int classify_explore(const ClassifyConsts& v, const float* scaled, const float* P, float wx, float wy, float wz, float R,
                             float half) {
   const float eps = 1e-3f, trunc = (float)v.trunc_d;

@@ -207,3 +207,16 @@ def test_reproject_pixel_matches_oracle(oracle, emul):
             assert np.array_equal(got, want), "variant %d frame %d: %d pixels differ" % (variant, f, int((got != want).sum()))
             changed += int((want != depth).sum())
     assert changed > 100000                      # the warp really moves pixels
+
+
+def test_division_by_1000_is_exact(emul):
+    """ScaleDepth's d * lambda / 1000.f (TSDFVolume.cpp:28) is computed as multiply + two FMAs on the device
+    (scale_depth_div1000): equal to the IEEE division for EVERY float the fast path accepts, and for values outside it
+    (which fall back to the division)."""
+    emul.emul_check_div1000.restype = C.c_longlong
+    emul.emul_check_div1000.argtypes = [C.c_float, C.c_float]
+    assert emul.emul_check_div1000(0.5, 262144.0) == 0           # all 159 383 552 floats of the fast path
+    assert emul.emul_check_div1000(0.0, 1e-30) == 0              # zero and denormals / tiny values
+    assert emul.emul_check_div1000(262144.0, 262160.0) == 0      # just past the fast path
+    assert emul.emul_check_div1000(1e-3, 0.5) == 0
+
