@@ -43,6 +43,7 @@ static int print_help() {
   std::cout << "    -dev <device> (default), -oni <oni_file>" << std::endl;
   std::cout << "B200 build only:" << std::endl;
   std::cout << "    --device <n> --max_blocks <n> --fusion <1..32> --bench_json <file>" << std::endl;
+  std::cout << "    --save_volume <file> / --load_volume <file[,file...]> : raw volume checkpoint after / before the integration" << std::endl;
   std::cout << "    --devices <a,b,...>             : partition the volume's blocks over several GPUs" << std::endl;
   std::cout << "    --voxel_size <m> (3/512) --tsdf_trunc <m> (0.03) --block_res <n> (64, fixed)" << std::endl;
   return 0;
@@ -58,6 +59,7 @@ struct App {
   double voxel_size = 0.0, tsdf_trunc = 0.0;               // 0 = the reference constants
   std::string bench_json;
 
+  std::string save_volume, load_volume;   // raw volume checkpoint written after / read before the integration
   CameraParam camera;
   Trajectory traj, seg_traj, pose_traj;
   std::vector<float> grids;
@@ -113,6 +115,24 @@ struct App {
       if (er_tsdf_set_fusion(vol, fusion)) return fail("set_fusion");
       if (ctr_num > 0 && er_tsdf_set_control_grids(vol, grids.data(), ctr_num, ctr_resolution, (float)ctr_length)) return fail("set_control_grids");
       if (ndev > 1 && er_tsdf_set_partition(vol, k, ndev)) return fail("set_partition");
+      // --load_volume a[,b,...]: resume from checkpoints; a partitioned volume keeps only the blocks it owns, so the
+      // per-device files of an earlier --devices run can be given to any number of devices
+      for (size_t pos = 0; pos < load_volume.size();) {
+        size_t end = load_volume.find(',', pos);
+        if (end == std::string::npos) end = load_volume.size();
+        if (end > pos && er_tsdf_load(vol, load_volume.substr(pos, end - pos).c_str())) return fail("er_tsdf_load");
+        pos = end + 1;
+      }
+    }
+    return true;
+  }
+
+  // --save_volume F: device k of n > 1 writes F.part<k>
+  bool save_checkpoint() {
+    if (save_volume.empty()) return true;
+    for (size_t k = 0; k < vols.size(); k++) {
+      const std::string fn = vols.size() == 1 ? save_volume : save_volume + ".part" + std::to_string(k);
+      if (er_tsdf_save(vols[k], fn.c_str())) return fail("er_tsdf_save");
     }
     return true;
   }
@@ -262,6 +282,8 @@ int main(int argc, char* argv[]) {
   parse_argument(argc, argv, "--voxel_size", app.voxel_size);
   parse_argument(argc, argv, "--tsdf_trunc", app.tsdf_trunc);
   parse_argument(argc, argv, "--block_res", app.block_res);
+  parse_argument(argc, argv, "--save_volume", app.save_volume);
+  parse_argument(argc, argv, "--load_volume", app.load_volume);
 
   std::cout << "Registration mode: On" << std::endl;
   const auto t0 = std::chrono::steady_clock::now();
@@ -269,6 +291,7 @@ int main(int argc, char* argv[]) {
   const auto t1 = std::chrono::steady_clock::now();
   if (ok) ok = app.run(src);
   const auto t2 = std::chrono::steady_clock::now();
+  if (ok) ok = app.save_checkpoint();
   if (ok) ok = app.save_world();
   std::cout << "Total " << app.frame_id << " frames processed." << std::endl;
   const auto t3 = std::chrono::steady_clock::now();

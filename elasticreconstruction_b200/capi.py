@@ -59,6 +59,8 @@ SIGNATURES = {
     "er_tsdf_block_keys": (C.c_int, [C.c_void_p, c_ip, C.c_int]),
     "er_tsdf_read_block": (C.c_int, [C.c_void_p, C.c_int, c_fp, c_fp]),
     "er_tsdf_extract": (C.c_int, [C.c_void_p, c_fp, C.c_size_t, c_szp]),
+    "er_tsdf_save": (C.c_int, [C.c_void_p, C.c_char_p]),
+    "er_tsdf_load": (C.c_int, [C.c_void_p, C.c_char_p]),
     "er_tsdf_event_record": (C.c_int, [C.c_void_p, C.c_int]),
     "er_tsdf_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_fp]),
     "er_tsdf_launch_count": (C.c_uint64, [C.c_void_p]),
@@ -349,6 +351,14 @@ class TSDFVolume:
         n = C.c_size_t()
         _check(lib().er_tsdf_extract(self._h, C.cast(C.c_void_p(hostbuf.ptr), c_fp), cap_rows, C.byref(n)))
         return n.value
+
+    def save(self, path: str):
+        """Raw volume checkpoint (er_tsdf_save)."""
+        _check(lib().er_tsdf_save(self._h, path.encode()))
+
+    def load(self, path: str):
+        """Add the blocks of a checkpoint to this volume (er_tsdf_load)."""
+        _check(lib().er_tsdf_load(self._h, path.encode()))
 
     def save_world(self, path: str) -> int:
         """Write world.pcd exactly as pcl::io::savePCDFile(binary) does for PointXYZI (TSDFVolume.cpp:130)."""

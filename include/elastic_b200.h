@@ -130,6 +130,14 @@ int er_tsdf_read_block(er_tsdf* v, int key, float* sdf, float* weight);
  * (global voxel indices as floats, tsdf) and the total count; order is unspecified as in the reference. */
 int er_tsdf_extract(er_tsdf* v, float* xyzi, size_t cap, size_t* n);
 
+/* Raw volume checkpoint (lets a later stage -- meshing, a resumed integration -- start from the device volume
+ * without the round trip through world.pcd): every allocated block as the reference's TSDFVolumeUnit (key, float sdf[64^3],
+ * float weight[64^3], k fastest; TSDFVolumeUnit.h:98-113).  er_tsdf_load adds the blocks of a checkpoint to a volume with the
+ * same voxel size and truncation (a block already present is overwritten); a partitioned volume takes only the blocks it
+ * owns, so per-rank checkpoints can be merged by loading them all into one unpartitioned volume. */
+int er_tsdf_save(er_tsdf* v, const char* path);
+int er_tsdf_load(er_tsdf* v, const char* path);
+
 /* Device-side timing on the handle's stream: record up to 16 events, read elapsed milliseconds. */
 int er_tsdf_event_record(er_tsdf* v, int slot);
 int er_tsdf_event_elapsed_ms(er_tsdf* v, int slot_a, int slot_b, float* ms);

@@ -117,6 +117,8 @@ int er_tsdf_extract(er_tsdf* v, float* xyzi, size_t cap, size_t* n) {
   return 0;
 }
 
+int er_tsdf_save(er_tsdf*, const char*) { return -1; }     // (checkpoints are exercised on the GPU only)
+int er_tsdf_load(er_tsdf*, const char*) { return -1; }
 void* er_host_alloc(size_t bytes) { return std::malloc(bytes ? bytes : 1); }
 void er_host_free(void* p) { std::free(p); }
 

@@ -306,3 +306,22 @@ def test_buildcorrespondence_cli_devices_equals_single_device(tmp_path):
             assert a.shape == b.shape and np.allclose(a, b, rtol=1e-9, atol=1e-6)
         else:
             assert outs["one"][k] == outs["many"][k], k
+
+
+def test_integrate_cli_checkpoint_resume(oracle, tmp_path):
+    """--save_volume after frames 1..3, --load_volume + --start_from 4 for the rest: the final world.pcd equals the
+    uninterrupted run's (the reference has no checkpoint; its world.pcd is the only state it can write)."""
+    sc = helpers.scene_room(n=6)
+    d = str(tmp_path)
+    synth.write_depth_container(os.path.join(d, "depth.raw"), sc["frames"])
+    synth.write_log(os.path.join(d, "traj.log"), sc["traj"])
+    base = [os.path.join(BIN, "Integrate"), "-oni", os.path.join(d, "depth.raw"), "--ref_traj", os.path.join(d, "traj.log")]
+    rc, out = run(base + ["--save_to", os.path.join(d, "full.pcd")], d)
+    assert rc == 0, out
+    rc, out = run(base + ["--save_to", os.path.join(d, "a.pcd"), "--end_at", "3", "--save_volume", os.path.join(d, "vol.ck")], d)
+    assert rc == 0 and os.path.getsize(os.path.join(d, "vol.ck")) > 1 << 20, out
+    rc, out = run(base + ["--save_to", os.path.join(d, "b.pcd"), "--start_from", "4", "--load_volume", os.path.join(d, "vol.ck")], d)
+    assert rc == 0, out
+    full = oracle.sort_world(synth.read_pcd_xyzi(os.path.join(d, "full.pcd")))
+    resumed = oracle.sort_world(synth.read_pcd_xyzi(os.path.join(d, "b.pcd")))
+    assert len(full) > 1000 and np.array_equal(full.view(np.uint32), resumed.view(np.uint32))

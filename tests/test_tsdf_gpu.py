@@ -299,3 +299,61 @@ def test_pool_overflow_stops_the_next_batch():
         vol.sync()
     with pytest.raises(capi.ElasticError, match="pool exhausted"):
         vol.integrate_batch(sc["frames"][2:4], sc["traj"][2:4])
+
+
+def test_volume_checkpoint_resume_merge_and_format(oracle, tmp_path):
+    """er_tsdf_save / er_tsdf_load (raw volume checkpoint): (a) integrate k frames, save, load into a fresh
+    volume, integrate the rest == the uninterrupted run, bit for bit; (b) the per-rank checkpoints of a partitioned volume
+    loaded into one unpartitioned volume == the unpartitioned run; (c) the file holds each block as the reference's
+    TSDFVolumeUnit arrays (k fastest)."""
+    sc = helpers.scene_room(n=6)
+    full = capi.TSDFVolume(max_blocks=512)
+    first = capi.TSDFVolume(max_blocks=512)
+    for f in range(6):
+        full.integrate(sc["frames"][f], sc["traj"][f])
+        if f < 3:
+            first.integrate(sc["frames"][f], sc["traj"][f])
+    ck = str(tmp_path / "vol.ck")
+    first.save(ck)
+    resumed = capi.TSDFVolume(max_blocks=512)
+    resumed.load(ck)
+    assert resumed.num_blocks() == first.num_blocks()
+    for f in range(3, 6):
+        resumed.integrate(sc["frames"][f], sc["traj"][f])
+    a, b = oracle.sort_world(full.extract()), oracle.sort_world(resumed.extract())
+    assert len(a) > 1000 and np.array_equal(a.view(np.uint32), b.view(np.uint32))
+    # (c) file format
+    raw = np.fromfile(ck, dtype=np.uint8)
+    assert bytes(raw[:7]) == b"ERTSDF1"
+    nb = int(raw[24:28].view(np.int32)[0])
+    assert nb == first.num_blocks() and len(raw) == 32 + nb * (8 + 8 * 64 ** 3)
+    key0 = int(raw[32:36].view(np.int32)[0])
+    blk = raw[40:40 + 8 * 64 ** 3].view(np.float32)
+    sdf, w = first.read_block(key0)
+    assert np.array_equal(blk[:64 ** 3], sdf) and np.array_equal(blk[64 ** 3:], w)
+    # (b) merge of partition checkpoints
+    parts = [capi.TSDFVolume(max_blocks=512) for _ in range(3)]
+    for r, p in enumerate(parts):
+        p.set_partition(r, 3)
+        for f in range(6):
+            p.integrate(sc["frames"][f], sc["traj"][f])
+        p.save(str(tmp_path / ("part%d.ck" % r)))
+    merged = capi.TSDFVolume(max_blocks=512)
+    for r in range(3):
+        merged.load(str(tmp_path / ("part%d.ck" % r)))
+    c = oracle.sort_world(merged.extract())
+    assert np.array_equal(a.view(np.uint32), c.view(np.uint32))
+    # a partitioned volume takes only its own blocks from a full checkpoint
+    full.save(ck)
+    mine = capi.TSDFVolume(max_blocks=512)
+    mine.set_partition(1, 3)
+    mine.load(ck)
+    assert mine.num_blocks() == parts[1].num_blocks()
+    # errors: wrong file, mismatching voxel size
+    with pytest.raises(capi.ElasticError, match="not a volume checkpoint"):
+        bad = str(tmp_path / "bad.ck")
+        open(bad, "wb").write(b"nope" * 20)
+        merged.load(bad)
+    other = capi.TSDFVolume(max_blocks=64, voxel=0.012)
+    with pytest.raises(capi.ElasticError, match="differ"):
+        other.load(ck)
