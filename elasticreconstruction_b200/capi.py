@@ -59,6 +59,8 @@ SIGNATURES = {
     "er_tsdf_block_keys": (C.c_int, [C.c_void_p, c_ip, C.c_int]),
     "er_tsdf_read_block": (C.c_int, [C.c_void_p, C.c_int, c_fp, c_fp]),
     "er_tsdf_extract": (C.c_int, [C.c_void_p, c_fp, C.c_size_t, c_szp]),
+    "er_tsdf_extract_begin": (C.c_int, [C.c_void_p, c_fp, C.c_size_t]),
+    "er_tsdf_extract_wait": (C.c_int, [C.c_void_p, c_szp]),
     "er_tsdf_save": (C.c_int, [C.c_void_p, C.c_char_p]),
     "er_tsdf_load": (C.c_int, [C.c_void_p, C.c_char_p]),
     "er_tsdf_event_record": (C.c_int, [C.c_void_p, C.c_int]),
@@ -350,6 +352,16 @@ class TSDFVolume:
         assert hostbuf.nbytes >= cap_rows * 16
         n = C.c_size_t()
         _check(lib().er_tsdf_extract(self._h, C.cast(C.c_void_p(hostbuf.ptr), c_fp), cap_rows, C.byref(n)))
+        return n.value
+
+    def extract_begin(self, hostbuf: "HostBuffer", cap_rows: int):
+        """Start SaveWorld's extraction into a page-locked buffer without blocking (er_tsdf_extract_begin)."""
+        assert hostbuf.nbytes >= cap_rows * 16
+        _check(lib().er_tsdf_extract_begin(self._h, C.cast(C.c_void_p(hostbuf.ptr), c_fp), cap_rows))
+
+    def extract_wait(self) -> int:
+        n = C.c_size_t()
+        _check(lib().er_tsdf_extract_wait(self._h, C.byref(n)))
         return n.value
 
     def save(self, path: str):

@@ -130,6 +130,14 @@ int er_tsdf_read_block(er_tsdf* v, int key, float* sdf, float* weight);
  * (global voxel indices as floats, tsdf) and the total count; order is unspecified as in the reference. */
 int er_tsdf_extract(er_tsdf* v, float* xyzi, size_t cap, size_t* n);
 
+/* The same without blocking: er_tsdf_extract_begin enqueues the compaction of the volume as it is after every frame handed
+ * in so far (frames handed in later do not affect it) and the copy of `cap` rows to xyzi (page-locked memory, er_host_alloc)
+ * on a stream of its own, so that the copy overlaps the next frames' host->device copies; er_tsdf_extract_wait blocks until
+ * the rows are home and returns their number (if it exceeds cap only the first cap rows were delivered).  One extraction
+ * may be outstanding per handle. */
+int er_tsdf_extract_begin(er_tsdf* v, float* xyzi, size_t cap);
+int er_tsdf_extract_wait(er_tsdf* v, size_t* n);
+
 /* Raw volume checkpoint (lets a later stage -- meshing, a resumed integration -- start from the device volume
  * without the round trip through world.pcd): every allocated block as the reference's TSDFVolumeUnit (key, float sdf[64^3],
  * float weight[64^3], k fastest; TSDFVolumeUnit.h:98-113).  er_tsdf_load adds the blocks of a checkpoint to a volume with the

@@ -41,6 +41,8 @@ class FakeVol:
     def inputs_consumed(self): pass
     def extract_count(self): return 1000
     def extract_into(self, buf, cap): return 1000
+    def extract_begin(self, buf, cap): pass
+    def extract_wait(self): return 1000
     def extract(self): return np.zeros((10, 4), np.float32)
     def profile_device(self, p, poses, n):
         return (0.0018 * n, 0.0019 * n, 0.005 * n)

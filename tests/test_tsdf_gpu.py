@@ -357,3 +357,28 @@ def test_volume_checkpoint_resume_merge_and_format(oracle, tmp_path):
     other = capi.TSDFVolume(max_blocks=64, voxel=0.012)
     with pytest.raises(capi.ElasticError, match="differ"):
         other.load(ck)
+
+
+def test_async_extract_equals_blocking_and_snapshots_the_state(oracle):
+    """er_tsdf_extract_begin / _wait: the rows equal er_tsdf_extract's, and frames handed in after _begin do not leak into
+    the extraction that was begun before them."""
+    sc = helpers.scene_room(n=4)
+    vol = capi.TSDFVolume(max_blocks=512)
+    vol.integrate_batch(sc["frames"][:2], sc["traj"][:2])
+    ref = oracle.sort_world(vol.extract())
+    cap = len(ref) + 1000
+    buf = capi.HostBuffer(cap * 16)
+    vol.extract_begin(buf, cap)
+    vol.integrate_batch(sc["frames"][2:4], sc["traj"][2:4])        # enqueued behind the extraction
+    n = vol.extract_wait()
+    got = oracle.sort_world(buf.array(np.float32, 4 * n).reshape(n, 4).copy())
+    assert n == len(ref) and np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+    with pytest.raises(capi.ElasticError, match="no extraction outstanding"):
+        vol.extract_wait()
+    # a second round on the same handle, now with all four frames
+    ref2 = oracle.sort_world(vol.extract())
+    big = capi.HostBuffer((len(ref2) + 10) * 16)
+    vol.extract_begin(big, len(ref2) + 10)
+    n2 = vol.extract_wait()
+    got2 = oracle.sort_world(big.array(np.float32, 4 * n2).reshape(n2, 4).copy())
+    assert n2 == len(ref2) and np.array_equal(got2.view(np.uint32), ref2.view(np.uint32)) and n2 > n
