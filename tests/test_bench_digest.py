@@ -59,3 +59,19 @@ def test_digest_sum_over_ranks_gloo():
         p.join(120)
         assert p.exitcode == 0
     assert q.get(timeout=5) is True
+
+
+def test_ctrlgrid_scene_is_consistent():
+    """The configs[3] inputs bench.py generates: pose[c] * seg[c*I + j] reproduces the world trajectory (what
+    CIntegrateApp::Init composes, IntegrateApp.cpp:68-75), seg_traj has the extra entry Init needs, every fragment has a
+    lattice, and the lattice of fragment 0 is the regular one up to the <= 1 cm displacement."""
+    from elasticreconstruction_b200 import synth
+    sc = bench.ctrlgrid_scene(200, interval=50)
+    assert sc["num"] == 4 and len(sc["seg"]) == 201 and sc["grids"].shape == (4, 9 ** 3, 3)
+    for f in range(200):
+        T = sc["pose"][f // 50] @ sc["seg"][f]
+        assert np.abs(T - sc["world"][f]).max() < 5e-7              # quantised to %.8f like the .log files
+    reg = synth.regular_lattice(8, 3.0)
+    assert np.abs(sc["grids"][0] - reg).max() <= 0.0100001
+    # camera inside the 6 m room, looking at walls within integration range for most pixels
+    assert np.all(sc["world"][:, :3, 3] > 0.9) and np.all(sc["world"][:, :3, 3] < 5.1)
