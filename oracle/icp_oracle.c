@@ -15,7 +15,11 @@
  * constructTransformationMatrix, default_convergence_criteria.hpp hasConverged, kdtree_flann.hpp with
  * flann::L2_Simple<float>, common/impl/transforms.hpp transformPointCloudWithNormals) from knowledge of those
  * sources; this file is therefore the DEFINITION the CUDA path is held to (tests cross-check its nearest
- * neighbour search against brute force and scipy.spatial.cKDTree and its 6x6 solve against numpy).  The Eigen
+ * neighbour search against brute force and scipy.spatial.cKDTree and its 6x6 solve against numpy).  The FLANN half IS
+ * pinned against real FLANN code since round 2: OpenCV bundles FLANN, cv2.flann_Index(algorithm=4) is the
+ * flann::KDTreeSingleIndex that pcl::KdTreeFLANN instantiates, and tests/test_oracle_icp.py
+ * (test_search_and_gate_against_a_real_flann_build) finds this file's search distances bit-equal to its exact search and
+ * the gate count of CorresApp.cpp:257-264 equal.  The Eigen
  * half of PCL's arithmetic IS pinned: oracle/eigen_check.cpp runs the Eigen 3.1.2 the reference vendors, and
  * tests/test_oracle_icp.py finds the Matrix4f products restated below bit-identical to it and the 6x6 solve within
  * 1.6e-10 relative of ATA.inverse() * ATb (no difference left after the narrowing to float).

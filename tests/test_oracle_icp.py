@@ -149,3 +149,39 @@ def test_solve6_against_eigen_inverse_times_rhs(oracle, pair):
         total += 6
     assert worst < 1e-8, worst
     assert float_diffs <= total // 100, (float_diffs, total)       # the float narrowing hides the difference almost always
+
+
+def test_search_and_gate_against_a_real_flann_build(oracle):
+    """The kd-tree half of what PCL does, against REAL FLANN code: OpenCV bundles FLANN, and `cv2.flann_Index` with
+    algorithm 4 is flann::KDTreeSingleIndex -- the index class pcl::KdTreeFLANN instantiates (leaf size 15, exact search:
+    unlimited checks, eps 0; PCL's L2_Simple and OpenCV's L2 accumulate ((dx^2 + dy^2) + dz^2) in float in the same order
+    for three dimensions).  On a full-size bench pair under its initial pose: every squared distance the oracle's search
+    returns inside the gate radius is BIT-EQUAL to FLANN's, the matched index is FLANN's except on exact distance ties,
+    and the gate count of CCorresApp::Registration (CorresApp.cpp:257-264) computed from FLANN's distances equals the
+    oracle's.  (This pins the search; PCL's own logic -- correspondence estimation, LLS, convergence -- stays restated.)"""
+    cv2 = pytest.importorskip("cv2")
+    (x0, n0), (x1, n1) = synth.make_local_fragment(0, 200000), synth.make_local_fragment(1, 200000)
+    T = synth.pair_init(0, 1)
+    # transformPointCloudWithNormals (CorresApp.cpp:250): double math, narrowed to float
+    q = (x1.astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+    index = cv2.flann_Index(x0, dict(algorithm=4, leaf_max_size=15))
+    ind, d2 = index.knnSearch(q, 1, params=dict(checks=-1, eps=0.0, sorted=True))
+    ind, d2 = ind.ravel(), d2.ravel()
+    tgt = oracle.OracleCloud(x0, n0, 0.03)
+    reg2 = 0.03 * 0.03
+    rng = np.random.default_rng(11)
+    ties = 0
+    for k in rng.choice(len(q), 20000, replace=False):
+        io, do = tgt.nn(q[k])
+        if d2[k] <= reg2:
+            assert io >= 0 and np.float32(do) == d2[k], (k, do, d2[k])
+            if io != ind[k]:                     # only legitimate on an exact tie
+                dd = x0[io].astype(np.float32) - q[k]
+                assert np.float32(np.float32(dd[0] * dd[0] + dd[1] * dd[1]) + dd[2] * dd[2]) == d2[k]
+                ties += 1
+        else:
+            assert io < 0 or do >= d2[k]
+    assert ties < 50
+    cnt_flann = int(np.count_nonzero(d2.astype(np.float64) < reg2))
+    src = oracle.OracleCloud(x1, n1, 0.03)
+    assert oracle.icp_count_inliers(tgt, src, T, 0.03) == cnt_flann and cnt_flann > 100000
