@@ -185,3 +185,33 @@ def test_search_and_gate_against_a_real_flann_build(oracle):
     cnt_flann = int(np.count_nonzero(d2.astype(np.float64) < reg2))
     src = oracle.OracleCloud(x1, n1, 0.03)
     assert oracle.icp_count_inliers(tgt, src, T, 0.03) == cnt_flann and cnt_flann > 100000
+
+
+def test_correspondence_selection_against_a_real_flann_build(oracle):
+    """CCorresApp::FindCorrespondence's selection (CorresApp.cpp:145-161) rebuilt from REAL FLANN results: transformed
+    source (transformPointCloudWithNormals: double math narrowed to float), flann::KDTreeSingleIndex 1-NN through OpenCV's
+    bundled FLANN, `dist^2 < dist_thresh^2 && NormalDot > normal_thresh` in the reference's float / double mix -- the
+    (target, source) list equals the oracle's, in source order; a target index may differ only where FLANN broke an exact
+    distance tie the other way."""
+    cv2 = pytest.importorskip("cv2")
+    (x0, n0), (x1, n1) = synth.make_local_fragment(2, 120000), synth.make_local_fragment(5, 120000)
+    T = synth.quantize_log(synth.pair_init(2, 5, max_rot_deg=0.2, max_trans=0.003))
+    R, t = T[:3, :3], T[:3, 3]
+    q = (x1.astype(np.float64) @ R.T + t).astype(np.float32)
+    nq = (n1.astype(np.float64) @ R.T).astype(np.float32)
+    ind, d2 = cv2.flann_Index(x0, dict(algorithm=4, leaf_max_size=15)).knnSearch(q, 1, params=dict(checks=-1, eps=0.0, sorted=True))
+    ind, d2 = ind.ravel(), d2.ravel()
+    tn = n0[ind]
+    dot = np.float32(np.float32(tn[:, 0] * nq[:, 0] + tn[:, 1] * nq[:, 1]) + tn[:, 2] * nq[:, 2])        # NormalDot, float
+    keep = (d2.astype(np.float64) < 0.015 * 0.015) & (dot.astype(np.float64) > 0.8660)
+    mine = np.stack([ind[keep], np.nonzero(keep)[0]], axis=1)
+    po, _ = oracle.icp_correspondences(oracle.OracleCloud(x0, n0, 0.03), oracle.OracleCloud(x1, n1, 0.03), T, 0.015, 0.8660)
+    assert len(po) > 50000 and len(po) == len(mine) and np.array_equal(po[:, 1], mine[:, 1])
+    differ = np.nonzero(po[:, 0] != mine[:, 0])[0]
+    assert len(differ) < 20
+    for r in differ:                             # exact ties only
+        k = po[r, 1]
+        a, b = x0[po[r, 0]] - q[k], x0[mine[r, 0]] - q[k]
+        da = np.float32(np.float32(a[0] * a[0] + a[1] * a[1]) + a[2] * a[2])
+        db = np.float32(np.float32(b[0] * b[0] + b[1] * b[1]) + b[2] * b[2])
+        assert da == db
