@@ -348,7 +348,44 @@ def ctrlgrid_leg(args, local, rank, world, barrier, capi, torch, dist):
            "reproject_note": "reproject_kernel + z-buffer reset/convert of one frame, event-bracketed on the stream; algorithmic "
                              "bytes 2 B read + 4 B atomicMin + 4+2 B convert per pixel = 3.7 MB/frame"}
     del vol
+    if rank == 0 and world == 1 and args.ctr_cpu_frames > 0:
+        out["cpu_baseline"] = ctrlgrid_cpu_leg(sc, traj, d_frames, args.ctr_cpu_frames)
     return out
+
+
+def ctrlgrid_cpu_leg(sc, traj, d_frames, n_cpu: int):
+    """The verbatim reference binary in ControlGrid mode (--pose_traj --seg_traj --ctr --num) on
+    the first fragments of the same scene; per-frame wall time of Execute(), which includes its serial Reproject
+    (IntegrateApp.cpp:228-269)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import pyoracle
+    if not os.path.exists(pyoracle.REF_INTEGRATE):
+        return None
+    I = sc["interval"]
+    num = max(1, n_cpu // I)
+    n = num * I
+    with tempfile.TemporaryDirectory() as d:
+        # (two frames fewer than the trajectories cover: the stream must end before the application's own exit condition
+        # -- frame id reaching the trajectory's length, IntegrateApp.cpp:200 -- for the shim to report its time stamps)
+        frames = d_frames[: n - 2].cpu().numpy().view(np.uint16)
+        synth.write_depth_container(os.path.join(d, "depth.raw"), frames)
+        synth.write_log(os.path.join(d, "seg.log"), sc["seg"][: n + 1])
+        synth.write_log(os.path.join(d, "pose.log"), sc["pose"][:num])
+        synth.write_ctr(os.path.join(d, "grids.ctr"), sc["grids"][:num])
+        tfile = os.path.join(d, "stamps.txt")
+        env = dict(os.environ, ER_SHIM_TIMING_FILE=tfile)
+        subprocess.run([pyoracle.REF_INTEGRATE, "-oni", os.path.join(d, "depth.raw"), "--seg_traj", os.path.join(d, "seg.log"),
+                        "--pose_traj", os.path.join(d, "pose.log"), "--ctr", os.path.join(d, "grids.ctr"), "--num", str(num),
+                        "--resolution", str(sc["res"]), "--length", str(sc["length"]), "--interval", str(I),
+                        "--save_to", os.path.join(d, "w.pcd")], cwd=d, env=env, stdout=subprocess.DEVNULL,
+                       stderr=subprocess.DEVNULL, check=True)
+        per = np.diff(np.loadtxt(tfile))
+    per = per[: n - 2]
+    skip = min(5, len(per) // 4)
+    fps = (len(per) - skip) / float(per[skip:].sum())
+    return {"value": fps, "unit": "frames/s", "cores": min(8, os.cpu_count() or 1), "kind": "reference",
+            "sample": "first %d frames (%d fragment(s)) of the same scene through the verbatim reference binary in --ctr mode, "
+                      "per-frame wall time of Execute() incl. its serial Reproject; %d warm-up frames dropped" % (n, num, skip)}
 
 
 # --------------------------------------------------------------------------------------------- main arm
@@ -374,6 +411,7 @@ def main():
     ap.add_argument("--ctr-frames", type=int, default=1000)
     ap.add_argument("--ctr-steps", type=int, default=3)
     ap.add_argument("--ctr-pool", type=int, default=4096)
+    ap.add_argument("--ctr-cpu-frames", type=int, default=100, help="frames of the ControlGrid scene timed on the reference binary (0 = skip)")
     ap.add_argument("--e2e-chunk", type=int, default=200, help="frames per H2D/all-gather chunk of the sharded feed (N > 1)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -92,7 +92,7 @@ sys.exit(bench.main())
 
 def test_main_arm_prints_one_json_line_with_the_contract_keys(tmp_path):
     argv = ["--steps", "1", "--warmup", "1", "--frames-per-step", "50", "--cpu-frames", "6", "--icp-fragments", "3", "--icp-points", "2000",
-            "--ctr-frames", "100", "--ctr-steps", "1"]
+            "--ctr-frames", "100", "--ctr-steps", "1", "--ctr-cpu-frames", "50"]
     script = tmp_path / "drive.py"
     script.write_text(DRIVER % dict(root=ROOT, argv=argv))
     p = subprocess.run([sys.executable, str(script)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, cwd=ROOT)
@@ -111,6 +111,7 @@ def test_main_arm_prints_one_json_line_with_the_contract_keys(tmp_path):
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] == 8
     assert d["icp"]["warmup_passes"] >= 3 and "roofline" in d["icp"] and d["icp"]["timed_passes"] >= 3
     assert d["e2e"]["d2h_bytes_per_step"] > 1000 and d["ctrlgrid"]["reproject_us_per_frame"] > 0
+    assert d["ctrlgrid"]["cpu_baseline"]["kind"] == "reference" and d["ctrlgrid"]["cpu_baseline"]["value"] > 1
 
 
 def test_reference_arm_line(tmp_path):

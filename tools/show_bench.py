@@ -12,7 +12,8 @@ print("  union:", d.get("union_check"))
 print("  replica:", d.get("replica"))
 if d.get("ctrlgrid"):
     c = d["ctrlgrid"]
-    print("  ctrlgrid %.0f frames/s, reproject %.2f us/frame, blocks %d" % (c["value"], c["reproject_us_per_frame"], c["allocated_blocks"]))
+    print("  ctrlgrid %.0f frames/s, reproject %.2f us/frame, blocks %d, cpu %s" % (
+        c["value"], c["reproject_us_per_frame"], c["allocated_blocks"], (c.get("cpu_baseline") or {}).get("value")))
 if d.get("icp"):
     i = d["icp"]
     print("  icp %.0f pair-it/s passes %s e2e %.0f cpu %s" % (i["value"], i["passes_ms"], i["e2e"]["value"], (i.get("cpu_baseline") or {}).get("value")))
