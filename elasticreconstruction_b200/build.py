@@ -61,7 +61,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
                     print(" ".join(cmd), flush=True)
                 subprocess.check_call(cmd)
             objs.append(o)
-        cmd = [_nvcc()] + ARCH + ["-shared", "-Xcompiler", "-fopenmp", "-o", LIB] + objs + ["-lcudart"]
+        cmd = [_nvcc()] + ARCH + ["-shared", "-Xcompiler", "-fopenmp", "-o", LIB] + objs + ["-lcudart", "-lcusolver"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)
@@ -69,14 +69,14 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
 
 
 def build_apps(force: bool = False, verbose: bool = False):
-    """The drop-in executables (apps/Integrate, apps/BuildCorrespondence): C++ hosts over the C ABI."""
+    """The drop-in executables (apps/Integrate, apps/BuildCorrespondence, apps/FragmentOptimizer): C++ hosts over the C ABI."""
     apps_dir = os.path.join(ROOT, "apps")
     outs = []
     if not os.path.isdir(apps_dir):
         return outs
     os.makedirs(BIN_DIR, exist_ok=True)
     hdrs = [os.path.join(apps_dir, f) for f in os.listdir(apps_dir) if f.endswith(".h")]
-    for name in ("Integrate", "BuildCorrespondence"):
+    for name in ("Integrate", "BuildCorrespondence", "FragmentOptimizer"):
         src = os.path.join(apps_dir, name + ".cpp")
         if not os.path.exists(src):
             continue

@@ -293,3 +293,64 @@ def read_pcd_xyzi(path: str) -> np.ndarray:
 def ensure_dir(p: str) -> str:
     os.makedirs(p, exist_ok=True)
     return p
+
+
+# --------------------------------------------------------------------------- FragmentOptimizer inputs
+def fragopt_initial_pose(i: int, max_rot_deg: float = 0.3, max_trans: float = 0.004) -> np.ndarray:
+    """Initial pose of fragment i in the fragment-0 volume frame: the true frame F_i times a small error that the
+    optimisation has to remove (fragment 0 stays the identity: it is the anchor, OptApp.cpp:459-464)."""
+    if i == 0:
+        return np.eye(4)
+    return fragment_frame(i) @ perturbation(5000 + i, max_rot_deg, max_trans)
+
+
+def write_xyzn(path: str, xyz: np.ndarray, nrm: np.ndarray) -> None:
+    """`cloud_bin_xyzn_<i>.xyzn` as BuildCorrespondence --save_xyzn writes it (CorresApp.cpp:100-108): %.6f x 6."""
+    with open(path, "w") as f:
+        for p, n in zip(np.asarray(xyz, dtype=np.float64), np.asarray(nrm, dtype=np.float64)):
+            f.write("%.6f %.6f %.6f %.6f %.6f %.6f\n" % (p[0], p[1], p[2], n[0], n[1], n[2]))
+
+
+def make_fragopt_dataset(out_dir: str, num: int = 4, n_points: int = 20_000, dist: float = 0.015,
+                         normal_cos: float = 0.866, pcd: bool = False, pairs=None, stride: int = 1):
+    """Everything `FragmentOptimizer` reads (FragmentOptimizer/FragmentOptimizer.cpp:52-76), for `num` synthetic
+    fragments: `traj.log` (one pose per fragment, use --interval 1) such that OptApp.cpp:55-70 yields the initial
+    poses of `fragopt_initial_pose`; `cloud_bin_xyzn_<i>.xyzn` (or `cloud_bin_<i>.pcd`); `reg_output.log` with one record
+    per pair (frame_ = number of correspondences) and `corres_<i>_<j>.txt` ("target_index source_index", ascending source
+    index: CorresApp.cpp:157,175-184) found by a 1-NN search under the TRUE relative pose with the distance / normal tests
+    of FindCorrespondence.  Returns a dict with the arrays (points as written, i.e. rounded to the file's 6 decimals)."""
+    from scipy.spatial import cKDTree
+    ensure_dir(out_dir)
+    clouds = []
+    for i in range(num):
+        xyz, nrm = make_local_fragment(i, n_points)
+        if pcd:
+            write_pcd_xyzrgbnormal(os.path.join(out_dir, "cloud_bin_%d.pcd" % i), xyz, nrm)
+        else:
+            write_xyzn(os.path.join(out_dir, "cloud_bin_xyzn_%d.xyzn" % i), xyz, nrm)
+            # what sscanf("%f") gives back from the %.6f text
+            xyz = np.array([["%.6f" % v for v in row] for row in xyz.astype(np.float64)], dtype=np.float64).astype(np.float32)
+            nrm = np.array([["%.6f" % v for v in row] for row in nrm.astype(np.float64)], dtype=np.float64).astype(np.float32)
+        clouds.append((xyz, nrm))
+    basepose = BASEPOSE
+    traj = [np.linalg.inv(basepose) @ fragopt_initial_pose(i) @ basepose for i in range(num)]
+    write_log(os.path.join(out_dir, "traj.log"), traj)
+    if pairs is None:
+        pairs = [(i, j) for i in range(num) for j in range(i + 1, num)]
+    recs, poses, corres = [], [], {}
+    for (i, j) in pairs:
+        T = np.linalg.inv(fragment_frame(i)) @ fragment_frame(j)
+        src = clouds[j][0].astype(np.float64) @ T[:3, :3].T + T[:3, 3]
+        sn = clouds[j][1].astype(np.float64) @ T[:3, :3].T
+        d, idx = cKDTree(clouds[i][0].astype(np.float64)).query(src)
+        ok = (d < dist) & (np.einsum("ij,ij->i", sn, clouds[i][1][idx].astype(np.float64)) > normal_cos)
+        s = np.nonzero(ok)[0][::stride]
+        c = np.stack([idx[s], s], axis=1).astype(np.int32)
+        corres[(i, j)] = c
+        with open(os.path.join(out_dir, "corres_%d_%d.txt" % (i, j)), "w") as f:
+            f.write("".join("%d %d\n" % (a, b) for a, b in c))
+        recs.append((i, j, len(c)))
+        poses.append(T)
+    write_log(os.path.join(out_dir, "reg_output.log"), poses, ids=recs)
+    return {"clouds": clouds, "traj": quantize_log(np.array(traj)), "pairs": pairs, "corres": corres,
+            "reg_poses": quantize_log(np.array(poses))}

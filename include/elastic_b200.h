@@ -225,6 +225,79 @@ int er_icp_event_elapsed_ms(int device, int slot_a, int slot_b, float* ms);
 uint64_t er_icp_launch_count(int device);
 int er_icp_sync(int device);
 
+/* ================================================================================================
+ * FragmentOptimizer  (class COptApp + class PointCloud, FragmentOptimizer/OptApp.{h,cpp}, PointCloud.{h,cpp};
+ * SURVEY.md section 8f #2).  The data-parallel parts -- the per-point lattice coordinates and their updates, and the
+ * assembly of the normal equations over all correspondences of all fragment pairs -- run on the device; the control
+ * flow of OptimizeSLAC / OptimizeRigid / OptimizeNonrigid, the lattice regulariser (729 small SVDs) and the file
+ * formats live in apps/FragmentOptimizer.cpp, a C++ host over exactly these calls.
+ *
+ * Index conventions are the reference's: fragments 0..num-1 are the RELATIVE indices after blacklisting
+ * (OptApp.cpp:31-47); a lattice has (resolution+1)^3 nodes, node (i,j,k) at i + j(res+1) + k(res+1)^2, three doubles
+ * each (nper = 3(res+1)^3); the SLAC unknown vector is [6 per fragment | nper] (matrix_size_ = 6 num + nper,
+ * OptApp.cpp:428), the rigid one [6 per fragment], the nonrigid one [nper per fragment].
+ * ============================================================================================== */
+typedef struct er_fragopt er_fragopt;
+
+er_fragopt* er_fragopt_create(int device, int num, int resolution, double length);   /* COptApp members, OptApp.cpp:126-128 */
+void er_fragopt_destroy(er_fragopt* h);
+
+/* PointCloud::LoadFromPCDFile / LoadFromXYZNFile after parsing (PointCloud.cpp:21-63): xyzn = n rows of
+ * x y z nx ny nz (rows with a NaN normal already dropped by the caller).  GetCoordinate (PointCloud.h:96-177) runs for
+ * every row; like the reference, loading stops at the first point outside [0, length)^3 ("Point out of bound"):
+ * *n_kept = number of points the cloud then holds (the failing one included, as the zero-filled record the reference
+ * leaves behind), and the call still succeeds.  All clouds must be set before er_fragopt_set_pairs. */
+int er_fragopt_set_cloud(er_fragopt* h, int l, const float* xyzn, size_t n, size_t* n_kept);
+
+/* COptApp::InitCorrespondences (OptApp.cpp:100-118) after parsing: pair p joins fragments idx0[p] and idx1[p]; its rows
+ * (index into cloud idx0[p], index into cloud idx1[p]) are rows[2*row_start[p] .. 2*row_start[p+1]).  The library keeps
+ * them on the device ordered by (pair, lattice cell of the first point, lattice cell of the second), the order in which
+ * the assembly kernels walk them. */
+int er_fragopt_set_pairs(er_fragopt* h, int npairs, const int* idx0, const int* idx1, const size_t* row_start,
+                         const int32_t* rows);
+
+/* PointCloud::UpdatePose for every fragment (PointCloud.h:70-83; OptApp.cpp:297,402,443): T = num row-major 4x4
+ * doubles, cast to float like pose.cast<float>(), applied to positions and normals. */
+int er_fragopt_update_pose(er_fragopt* h, const double* T);
+/* PointCloud::UpdateAllNormal (PointCloud.h:37-41; OptApp.cpp:151-153): ctr = num*nper doubles. */
+int er_fragopt_update_normals(er_fragopt* h, const double* ctr);
+/* PointCloud::UpdateAllPointPN (PointCloud.h:43-51; OptApp.cpp:660-663): expand_ctr = num*nper doubles. */
+int er_fragopt_update_points_pn(er_fragopt* h, const double* expand_ctr);
+/* Current position and normal of every point of fragment l (n rows of x y z nx ny nz); UpdatePoint under `ctr`
+ * (PointCloud.h:85-94, used by SavePoints, OptApp.cpp:905-907) when ctr != NULL: then xyz = the warped position. */
+int er_fragopt_get_points(er_fragopt* h, int l, float* xyzn, size_t cap_rows, const double* ctr);
+
+/* Data term of one SLAC iteration (the pair loop of OptimizeSLAC, OptApp.cpp:473-570): rot_t = pose_rot_t_, num
+ * row-major 3x3 doubles.  The dense upper triangle of JJ (matrix_size_^2 doubles) stays on the device; Jb
+ * (matrix_size_ doubles) and the data error score come back.  One kernel over all correspondences: a 128-thread CTA
+ * stages 128 Jacobian rows (60 entries each) in shared memory and accumulates their outer products in 4x4 register
+ * tiles; sums leave a CTA only when the 60 column indices change (the sorted order makes that rare). */
+int er_fragopt_slac_assemble(er_fragopt* h, const double* rot_t, double* Jb, double* score);
+/* Solves (base + JJ_data) x = rhs by a dense Cholesky factorisation on the device (the reference:
+ * CholmodSupernodalLLT on thisJJ.sparseView(), OptApp.cpp:574-577,639).  base = the regulariser part, dense row-major
+ * matrix_size_^2 doubles of which the upper triangle is read (baseJJ * default_weight plus the six ones of
+ * OptApp.cpp:456-464); NULL = the matrix given last time. */
+int er_fragopt_slac_solve(er_fragopt* h, const double* base, const double* rhs, double* x);
+/* The assembled data term, upper triangle of a row-major matrix_size_^2 matrix (tests, diagnostics). */
+int er_fragopt_slac_get_jj(er_fragopt* h, double* jj);
+
+/* Data term of one rigid iteration (OptApp.cpp:312-385): JJ = upper triangle of a row-major (6 num)^2 matrix,
+ * Jb = 6 num doubles, score = sum b^2.  (The six ones every pair adds to the first six diagonal entries,
+ * OptApp.cpp:323-325, are the caller's.) */
+int er_fragopt_rigid_assemble(er_fragopt* h, double* JJ, double* Jb, double* score);
+
+/* Data term of one nonrigid outer iteration (OptApp.cpp:159-206) as dense 3*8 x 3*8 blocks is not what the
+ * reference stores; it is delivered in coordinate form instead: for every (pair, cell, cell) segment the 24x24
+ * blocks ii, jj, ij.  Not implemented in this round. */
+
+/* Timing / accounting like the other paths (events on the handle's stream). */
+int er_fragopt_event_record(er_fragopt* h, int slot);
+int er_fragopt_event_elapsed_ms(er_fragopt* h, int slot_a, int slot_b, float* ms);
+uint64_t er_fragopt_launch_count(const er_fragopt* h);
+int er_fragopt_sync(er_fragopt* h);
+/* Device time of the last er_fragopt_slac_assemble's assembly kernel alone, and the number of segment flushes it made. */
+int er_fragopt_last_assemble_stats(er_fragopt* h, float* kernel_ms, uint64_t* rows, uint64_t* flushes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -15,6 +15,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
 REF_INTEGRATE = os.path.join(_HERE, "_ref", "Integrate_ref")
 REF_INTEGRATE_12MM = os.path.join(_HERE, "_ref", "Integrate_ref_12mm")     # unit_length_ patched to 0.012 (Makefile: ref12)
+REF_FRAGOPT = os.path.join(_HERE, "_ref", "FragmentOptimizer_ref")       # verbatim FragmentOptimizer (Makefile: fragopt)
 EIGEN_CHECK = os.path.join(_HERE, "_ref", "libeigen_check.so")              # the reference's vendored Eigen 3.1.2 (Makefile: eigen)
 
 _lib = None
@@ -32,6 +33,8 @@ def build(force: bool = False) -> None:
         subprocess.check_call(["make", "-C", _HERE, "-s", "ref12"])
     if os.path.isdir("/root/reference/FragmentOptimizer/external/Eigen") and (force or not os.path.exists(EIGEN_CHECK)):
         subprocess.check_call(["make", "-C", _HERE, "-s", "eigen"])
+    if os.path.isdir("/root/reference/FragmentOptimizer") and (force or not os.path.exists(REF_FRAGOPT)):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "fragopt"])
 
 
 def lib():
@@ -304,3 +307,16 @@ def run_reference_integrate(args, cwd=None, timing: bool = False, binary: str = 
         if line.startswith("[shim]") and "ms_per_frame=" in line:
             ms = float(line.split("ms_per_frame=")[1])
     return p.stdout, ms
+
+
+def run_reference_fragopt(args, cwd=None, threads: int = None, timeout: float = 3600.0):
+    """Run the verbatim reference FragmentOptimizer (oracle/_ref/FragmentOptimizer_ref) in `cwd` (it writes pose.log,
+    output.ctr ... there).  Its pair loop sums per-pair matrices under an OpenMP critical section in arrival order
+    (OptApp.cpp:562-569), so results vary at rounding level from run to run; threads=1 (OMP_THREAD_LIMIT) fixes the
+    order.  Returns stdout+stderr."""
+    env = dict(os.environ)
+    if threads is not None:
+        env["OMP_THREAD_LIMIT"] = str(threads)
+    p = subprocess.run([REF_FRAGOPT] + list(args), cwd=cwd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, check=True, timeout=timeout)
+    return p.stdout
