@@ -85,6 +85,23 @@ SIGNATURES = {
     "er_icp_event_elapsed_ms": (C.c_int, [C.c_int, C.c_int, C.c_int, c_fp]),
     "er_icp_launch_count": (C.c_uint64, [C.c_int]),
     "er_icp_sync": (C.c_int, [C.c_int]),
+    "er_fragopt_create": (C.c_void_p, [C.c_int, C.c_int, C.c_int, C.c_double]),
+    "er_fragopt_destroy": (None, [C.c_void_p]),
+    "er_fragopt_set_cloud": (C.c_int, [C.c_void_p, C.c_int, c_fp, C.c_size_t, c_szp]),
+    "er_fragopt_set_pairs": (C.c_int, [C.c_void_p, C.c_int, c_ip, c_ip, c_szp, c_i32p]),
+    "er_fragopt_update_pose": (C.c_int, [C.c_void_p, c_dp]),
+    "er_fragopt_update_normals": (C.c_int, [C.c_void_p, c_dp]),
+    "er_fragopt_update_points_pn": (C.c_int, [C.c_void_p, c_dp]),
+    "er_fragopt_get_points": (C.c_int, [C.c_void_p, C.c_int, c_fp, C.c_size_t, c_dp]),
+    "er_fragopt_slac_assemble": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp]),
+    "er_fragopt_slac_solve": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp]),
+    "er_fragopt_slac_get_jj": (C.c_int, [C.c_void_p, c_dp]),
+    "er_fragopt_rigid_assemble": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp]),
+    "er_fragopt_event_record": (C.c_int, [C.c_void_p, C.c_int]),
+    "er_fragopt_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_fp]),
+    "er_fragopt_launch_count": (C.c_uint64, [C.c_void_p]),
+    "er_fragopt_sync": (C.c_int, [C.c_void_p]),
+    "er_fragopt_last_assemble_stats": (C.c_int, [C.c_void_p, c_fp, c_u64p, c_u64p]),
 }
 
 
@@ -542,3 +559,118 @@ def icp_event_elapsed_ms(device: int, a: int, b: int) -> float:
 
 def icp_launch_count(device: int) -> int:
     return int(lib().er_icp_launch_count(device))
+
+
+# ================================================================================================== FragmentOptimizer
+class FragOpt:
+    """COptApp's device-side state (include/elastic_b200.h, er_fragopt_*): the fragments' points with their lattice
+    coordinates, the correspondences of all pairs, and the assembly of the SLAC / rigid normal equations.
+    `library` = an alternative ctypes library exporting the same entry points (the CPU emulation of the tests)."""
+
+    def __init__(self, num: int, resolution: int = 8, length: float = 3.0, device: int = 0, library=None):
+        self._L = library if library is not None else lib()
+        if library is not None:
+            for name, (res, args) in SIGNATURES.items():
+                if name.startswith("er_fragopt_") or name == "er_last_error":
+                    fn = getattr(library, name)
+                    fn.restype, fn.argtypes = res, args
+        self.num, self.res, self.length = int(num), int(resolution), float(length)
+        self.nper = (self.res + 1) ** 3 * 3
+        self.M = 6 * self.num + self.nper
+        self.sizes = [0] * self.num
+        h = self._L.er_fragopt_create(int(device), self.num, self.res, self.length)
+        if not h:
+            raise ElasticError("er_fragopt_create failed: " + self._L.er_last_error().decode("utf-8", "replace"))
+        self._h = C.c_void_p(h)
+
+    def _check(self, rc):
+        if rc != 0:
+            raise ElasticError(self._L.er_last_error().decode("utf-8", "replace"))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.er_fragopt_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_cloud(self, l: int, xyzn) -> int:
+        a = np.ascontiguousarray(xyzn, dtype=np.float32).reshape(-1, 6)
+        kept = C.c_size_t()
+        self._check(self._L.er_fragopt_set_cloud(self._h, int(l), _fp(a), len(a), C.byref(kept)))
+        self.sizes[l] = kept.value
+        return kept.value
+
+    def set_pairs(self, pairs, corres):
+        """pairs = [(i, j)], corres = list of [m,2] int arrays (index into cloud i, index into cloud j)."""
+        n = len(pairs)
+        i0 = np.ascontiguousarray([p[0] for p in pairs], dtype=np.int32)
+        i1 = np.ascontiguousarray([p[1] for p in pairs], dtype=np.int32)
+        start = np.zeros(n + 1, dtype=np.uintp)
+        for k, c in enumerate(corres):
+            start[k + 1] = start[k] + len(c)
+        rows = (np.concatenate([np.asarray(c, dtype=np.int32).reshape(-1, 2) for c in corres]) if n and start[n]
+                else np.zeros((1, 2), dtype=np.int32))
+        rows = np.ascontiguousarray(rows, dtype=np.int32)
+        self._check(self._L.er_fragopt_set_pairs(self._h, n, i0.ctypes.data_as(c_ip), i1.ctypes.data_as(c_ip),
+                                                 start.ctypes.data_as(c_szp), rows.ctypes.data_as(c_i32p)))
+
+    def update_pose(self, T):
+        T = np.ascontiguousarray(T, dtype=np.float64).reshape(self.num, 16)
+        self._check(self._L.er_fragopt_update_pose(self._h, _dp(T)))
+
+    def update_normals(self, ctr):
+        c = np.ascontiguousarray(ctr, dtype=np.float64).reshape(self.num * self.nper)
+        self._check(self._L.er_fragopt_update_normals(self._h, _dp(c)))
+
+    def update_points_pn(self, ctr):
+        c = np.ascontiguousarray(ctr, dtype=np.float64).reshape(self.num * self.nper)
+        self._check(self._L.er_fragopt_update_points_pn(self._h, _dp(c)))
+
+    def points(self, l: int, ctr=None) -> np.ndarray:
+        out = np.empty((max(self.sizes[l], 1), 6), dtype=np.float32)
+        c = None if ctr is None else np.ascontiguousarray(ctr, dtype=np.float64).reshape(self.num * self.nper)
+        self._check(self._L.er_fragopt_get_points(self._h, int(l), _fp(out), self.sizes[l], None if c is None else _dp(c)))
+        return out[: self.sizes[l]]
+
+    def slac_assemble(self, rot_t):
+        """Returns (Jb [M], score); the matrix stays on the device (slac_jj() copies it out)."""
+        r = np.ascontiguousarray(rot_t, dtype=np.float64).reshape(self.num * 9)
+        Jb = np.empty(self.M, dtype=np.float64)
+        score = C.c_double()
+        self._check(self._L.er_fragopt_slac_assemble(self._h, _dp(r), _dp(Jb), C.byref(score)))
+        return Jb, score.value
+
+    def slac_jj(self) -> np.ndarray:
+        jj = np.empty((self.M, self.M), dtype=np.float64)
+        self._check(self._L.er_fragopt_slac_get_jj(self._h, _dp(jj)))
+        return jj
+
+    def slac_solve(self, base, rhs) -> np.ndarray:
+        b = None if base is None else np.ascontiguousarray(base, dtype=np.float64).reshape(self.M * self.M)
+        r = np.ascontiguousarray(rhs, dtype=np.float64).reshape(self.M)
+        x = np.empty(self.M, dtype=np.float64)
+        self._check(self._L.er_fragopt_slac_solve(self._h, None if b is None else _dp(b), _dp(r), _dp(x)))
+        return x
+
+    def rigid_assemble(self):
+        n6 = 6 * self.num
+        JJ = np.empty((n6, n6), dtype=np.float64)
+        Jb = np.empty(n6, dtype=np.float64)
+        score = C.c_double()
+        self._check(self._L.er_fragopt_rigid_assemble(self._h, _dp(JJ), _dp(Jb), C.byref(score)))
+        return JJ, Jb, score.value
+
+    def assemble_stats(self):
+        ms = C.c_float()
+        rows = C.c_uint64()
+        fl = C.c_uint64()
+        self._check(self._L.er_fragopt_last_assemble_stats(self._h, C.byref(ms), C.byref(rows), C.byref(fl)))
+        return ms.value, rows.value, fl.value
+
+    def launch_count(self) -> int:
+        return int(self._L.er_fragopt_launch_count(self._h))

@@ -149,3 +149,38 @@ def run_scene(vol, sc, mul=None):
         traj = compose_traj(sc["pose_traj"], sc["seg_traj"], sc["interval"], mul)
         return run_app(vol, sc["frames"], traj, sc["seg_traj"], sc["grids"], sc["res"], sc["length"], sc["interval"])
     return run_app(vol, sc["frames"], sc["traj"])
+
+
+# ----------------------------------------------------------------------------------------------- FragmentOptimizer cases
+FRAGOPT_CASES = {
+    # name: (num, points per fragment, extra flags, pcd input, blacklist)
+    "three": dict(num=3, n_points=6000, pcd=False, blacklist=None, flags=["--iteration", "2"]),
+    "four_pcd_blacklist": dict(num=4, n_points=4000, pcd=True, blacklist=[3], flags=["--iteration", "2", "--weight", "0.5"]),
+}
+
+
+def fragopt_case(name: str, out_dir: str):
+    """Writes the inputs of one FragmentOptimizer case under out_dir/data/ and returns (dataset dict, argv without the
+    mode flag).  The data set is deterministic (synth.make_fragopt_dataset)."""
+    import os
+    from elasticreconstruction_b200 import synth
+    c = FRAGOPT_CASES[name]
+    data = os.path.join(out_dir, "data") + os.sep
+    d = synth.make_fragopt_dataset(data, num=c["num"], n_points=c["n_points"], pcd=c["pcd"])
+    args = ["--rgbdslam", data + "traj.log", "--registration", data + "reg_output.log", "--dir", data, "--num", str(c["num"]),
+            "--interval", "1", "--blacklistpair", "1000"] + list(c["flags"])
+    if c["blacklist"]:
+        with open(os.path.join(out_dir, "blacklist.txt"), "w") as f:
+            f.write("# fragments to drop\n" + "".join("%d\n" % b for b in c["blacklist"]))
+        args += ["--blacklist", os.path.join(out_dir, "blacklist.txt")]
+    return d, args
+
+
+def read_log_poses(path: str):
+    import numpy as np
+    L = open(path).read().split("\n")
+    out, i = [], 0
+    while i + 4 < len(L):
+        out.append([[float(x) for x in L[i + 1 + r].split()] for r in range(4)])
+        i += 5
+    return np.array(out, dtype=np.float64)

@@ -1,0 +1,200 @@
+"""FragmentOptimizer path on the CPU (no GPU):
+
+* the numpy restatement oracle/fragopt_oracle.py against the VERBATIM reference binary's results
+  (tests/golden/fragopt_golden.npz, written by tests/golden/make_golden_fragopt.py; and live where oracle/_ref exists);
+* the product's kernel arithmetic (csrc/er_fragopt_math.h) re-enacted thread by thread by tests/emul/fragopt_emul.cpp:
+  point set-up and updates bit for bit against the oracle, the assembled SLAC / rigid normal equations within rounding
+  of the oracle's, independent of how the correspondences are split over CTAs;
+* apps/FragmentOptimizer.cpp linked against that emulation: pose.log / output.ctr against the reference binary's.
+
+Tolerances: the reference prints poses with 8 and lattices with 10 decimals, and sums its per-pair matrices in arrival
+order, so two runs of the reference itself differ at rounding level; 2e-8 / 2e-9 absolute is the print resolution plus
+that noise.  (north_star's bar for a pose is 1e-5 Frobenius.)"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CSRC = os.path.join(ROOT, "elasticreconstruction_b200", "csrc")
+OUT = os.path.join(ROOT, "tests", "emul", "_build")
+GOLDEN = os.path.join(ROOT, "tests", "golden", "fragopt_golden.npz")
+POSE_TOL, CTR_TOL = 2e-8, 2e-9
+
+
+def _stale(target, deps):
+    return not os.path.exists(target) or os.path.getmtime(target) < max(os.path.getmtime(p) for p in deps)
+
+
+@pytest.fixture(scope="module")
+def emul():
+    os.makedirs(OUT, exist_ok=True)
+    lib = os.path.join(OUT, "libfragopt_emul.so")
+    srcs = [os.path.join(ROOT, "tests", "emul", "fragopt_emul.cpp"), os.path.join(CSRC, "er_host_math.cpp")]
+    deps = srcs + [os.path.join(CSRC, "er_fragopt_math.h"), os.path.join(ROOT, "include", "elastic_b200.h")]
+    if _stale(lib, deps):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared",
+                               "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-I", "/usr/local/cuda/include"] + srcs + ["-o", lib])
+    exe = os.path.join(OUT, "FragmentOptimizer_emul")
+    app = os.path.join(ROOT, "apps", "FragmentOptimizer.cpp")
+    if _stale(exe, [app, os.path.join(ROOT, "apps", "er_io.h"), lib]):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"),
+                               "-I", os.path.join(ROOT, "apps"), app, "-o", exe, "-L", OUT, "-lfragopt_emul", "-Wl,-rpath," + OUT])
+    return {"lib": C.CDLL(lib), "exe": exe}
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN)
+
+
+def case_arrays(name, d):
+    import fragopt_oracle as fo
+    c = helpers.FRAGOPT_CASES[name]
+    keep = [i for i in range(c["num"]) if not (c["blacklist"] and i in c["blacklist"])]
+    rel = {a: r for r, a in enumerate(keep)}
+    xyzn = [np.concatenate([d["clouds"][i][0], d["clouds"][i][1]], axis=1) for i in keep]
+    # InitCorrespondences: blacklisted ids and ids >= the REDUCED fragment count are dropped (OptApp.cpp:104-106)
+    pairs = [(i, j) for (i, j) in d["pairs"] if i in rel and j in rel and i < len(keep) and j < len(keep) and len(d["corres"][(i, j)]) >= 1000]
+    corres = [d["corres"][p] for p in pairs]
+    ipose = fo.initial_poses(d["traj"], keep, 1, 3.0)
+    return xyzn, [(rel[i], rel[j]) for (i, j) in pairs], corres, ipose, c
+
+
+def flag(c, name, default):
+    return type(default)(c["flags"][c["flags"].index(name) + 1]) if name in c["flags"] else default
+
+
+@pytest.mark.parametrize("name", list(helpers.FRAGOPT_CASES))
+@pytest.mark.parametrize("mode", ["slac", "rigid"])
+def test_numpy_oracle_matches_reference_binary(golden, tmp_path, name, mode):
+    import fragopt_oracle as fo
+    d, _ = helpers.fragopt_case(name, str(tmp_path))
+    xyzn, pairs, corres, ipose, c = case_arrays(name, d)
+    it = flag(c, "--iteration", 5)
+    if mode == "slac":
+        pose, ctr = fo.optimize_slac(xyzn, pairs, corres, ipose, iterations=it, weight=flag(c, "--weight", 1.0), num_before_blacklist=c["num"])
+    else:
+        pose, ctr = fo.optimize_rigid(xyzn, pairs, corres, ipose, iterations=it)
+    assert np.abs(pose - golden["%s_%s_pose" % (name, mode)]).max() <= POSE_TOL
+    assert np.abs(ctr - golden["%s_%s_ctr" % (name, mode)]).max() <= CTR_TOL
+
+
+@pytest.mark.parametrize("name", list(helpers.FRAGOPT_CASES))
+@pytest.mark.parametrize("mode", ["slac", "rigid"])
+def test_emulated_executable_matches_reference_binary(oracle, emul, golden, tmp_path, name, mode):
+    d = str(tmp_path)
+    _, args = helpers.fragopt_case(name, d)
+    p = subprocess.run([emul["exe"]] + args + ["--" + mode, "--bench_json", os.path.join(d, "t.json")], cwd=d, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout
+    pose = helpers.read_log_poses(os.path.join(d, "pose.log"))
+    ctr = np.loadtxt(os.path.join(d, "output.ctr"))
+    assert np.abs(pose - golden["%s_%s_pose" % (name, mode)]).max() <= POSE_TOL
+    assert np.abs(ctr - golden["%s_%s_ctr" % (name, mode)]).max() <= CTR_TOL
+    scores = [float(l.split(":")[1]) for l in p.stdout.splitlines() if "rror score is" in l]
+    assert np.allclose(scores, golden["%s_%s_scores" % (name, mode)], atol=0.0101)          # printed with two decimals
+    if os.path.exists(oracle.REF_FRAGOPT):                                                   # and live, where the reference is built
+        os.rename(os.path.join(d, "pose.log"), os.path.join(d, "mine_pose.log"))
+        oracle.run_reference_fragopt(args + ["--" + mode], cwd=d)
+        assert np.abs(pose - helpers.read_log_poses(os.path.join(d, "pose.log"))).max() <= POSE_TOL
+        assert np.abs(ctr - np.loadtxt(os.path.join(d, "output.ctr"))).max() <= CTR_TOL
+
+
+def test_emulated_kernels_against_the_oracle(emul, tmp_path):
+    """API level: the emulated kernels (same header as the CUDA ones) against the numpy restatement."""
+    import fragopt_oracle as fo
+    from elasticreconstruction_b200 import capi
+    d, _ = helpers.fragopt_case("three", str(tmp_path))
+    xyzn, pairs, corres, ipose, _ = case_arrays("three", d)
+    num = len(xyzn)
+    L = fo.Lattice(8, 3.0)
+    M = 6 * num + L.nper
+    clouds = [fo.Cloud(L, c) for c in xyzn]
+    g = capi.FragOpt(num, 8, 3.0, library=emul["lib"])
+    for l in range(num):
+        assert g.set_cloud(l, xyzn[l]) == len(xyzn[l])
+    g.set_pairs(pairs, corres)
+    # loading: positions and the divided normal
+    for l in range(num):
+        pts = g.points(l)
+        assert np.array_equal(pts[:, :3], clouds[l].p) and np.array_equal(pts[:, 3:], clouds[l].n)
+    # UpdatePose, bit for bit
+    g.update_pose(ipose)
+    for l in range(num):
+        clouds[l].update_pose(ipose[l])
+        pts = g.points(l)
+        assert np.array_equal(pts[:, :3].view(np.uint32), clouds[l].p.view(np.uint32))
+        assert np.array_equal(pts[:, 3:].view(np.uint32), clouds[l].n.view(np.uint32))
+    # SLAC normal equations
+    rot_t = np.array([ipose[l][:3, :3].T for l in range(num)])
+    JJ, Jb, score = fo.slac_normal_equations(clouds, pairs, corres, num, rot_t, M)
+    gJb, gscore = g.slac_assemble(rot_t)
+    gJJ = g.slac_jj()
+    scale = np.abs(JJ).max()
+    assert np.array_equal(gJJ, np.triu(gJJ))
+    assert np.abs(gJJ - JJ).max() <= 1e-11 * scale
+    assert np.abs(gJb - Jb).max() <= 1e-11 * np.abs(Jb).max() and abs(gscore - score) <= 1e-11 * score
+    _, rows, flushes = g.assemble_stats()
+    assert rows == sum(len(c) for c in corres) and 0 < flushes < rows / 8          # the sorted order keeps segments long
+    # the split of the sorted list over CTAs does not matter
+    for ctas in ("1", "3", "64"):
+        os.environ["ER_FRAGOPT_EMUL_CTAS"] = ctas
+        try:
+            g2 = capi.FragOpt(num, 8, 3.0, library=emul["lib"])
+        finally:
+            del os.environ["ER_FRAGOPT_EMUL_CTAS"]
+        for l in range(num):
+            g2.set_cloud(l, xyzn[l])
+        g2.set_pairs(pairs, corres)
+        g2.update_pose(ipose)
+        Jb2, s2 = g2.slac_assemble(rot_t)
+        assert np.abs(g2.slac_jj() - JJ).max() <= 1e-11 * scale and np.abs(Jb2 - Jb).max() <= 1e-11 * np.abs(Jb).max()
+    # solve against numpy
+    B = fo.base_jj(L, num, M, num * 1.0)
+    rhs = Jb + 0.01 * np.cos(np.arange(M))
+    A = B + JJ
+    x = g.slac_solve(B, rhs)
+    assert np.abs(x - np.linalg.solve(A + np.triu(A, 1).T, rhs)).max() <= 1e-9 * max(1.0, np.abs(x).max())
+    # UpdateAllPointPN under a warped lattice, bit for bit
+    lat = np.array([[i * L.unit_d, j * L.unit_d, k * L.unit_d] for k in range(L.r1) for j in range(L.r1) for i in range(L.r1)])
+    lat = lat + 0.004 * np.sin(3.0 * lat[:, [1, 2, 0]])
+    ex = np.concatenate([lat @ ipose[l][:3, :3].T + ipose[l][:3, 3] for l in range(num)]).reshape(-1)
+    g.update_points_pn(ex)
+    for l in range(num):
+        clouds[l].update_point_pn(ex[l * L.nper:(l + 1) * L.nper])
+        pts = g.points(l)
+        assert np.array_equal(pts[:, :3].view(np.uint32), clouds[l].p.view(np.uint32))
+        assert np.array_equal(pts[:, 3:].view(np.uint32), clouds[l].n.view(np.uint32))
+        warped = g.points(l, ctr=ex)[:, :3]
+        assert np.array_equal(warped, clouds[l].warped(ex[l * L.nper:(l + 1) * L.nper]).astype(np.float32))
+    # rigid normal equations on the updated points
+    rJJ, rJb, rscore = fo.rigid_normal_equations(clouds, pairs, corres, num)
+    qJJ, qJb, qscore = g.rigid_assemble()
+    assert np.abs(qJJ - rJJ).max() <= 1e-11 * np.abs(rJJ).max() and np.abs(qJb - rJb).max() <= 1e-11 * np.abs(rJb).max()
+    assert abs(qscore - rscore) <= 1e-11 * rscore
+
+
+def test_out_of_bound_point_stops_loading(emul):
+    """PointCloud.cpp:37-40: the first point outside [0, length)^3 ends the cloud (it stays as a zero-filled record)."""
+    from elasticreconstruction_b200 import capi
+    g = capi.FragOpt(1, 8, 3.0, library=emul["lib"])
+    xyzn = np.array([[1, 1, 1, 0, 0, 1], [2, 2, 2, 0, 1, 0], [3.0, 1, 1, 1, 0, 0], [1, 2, 1, 1, 0, 0]], dtype=np.float32)
+    assert g.set_cloud(0, xyzn) == 3
+    xyzn[2, 0] = -0.001
+    g2 = capi.FragOpt(1, 8, 3.0, library=emul["lib"])
+    assert g2.set_cloud(0, xyzn) == 3
+    xyzn[2, 0] = 2.999
+    g3 = capi.FragOpt(1, 8, 3.0, library=emul["lib"])
+    assert g3.set_cloud(0, xyzn) == 4
+
+
+def test_executable_help_and_missing_mode(emul, tmp_path):
+    p = subprocess.run([emul["exe"]], stdout=subprocess.PIPE, text=True)
+    assert p.returncode == 0 and "--blasklist <blacklist_file>" in p.stdout and "--slac" in p.stdout
+    p = subprocess.run([emul["exe"], "--num", "2"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=str(tmp_path))
+    assert p.returncode == 2 and "not implemented" in p.stdout
