@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- headline benchmark of the B200-native hot paths (contract: see the task brief).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--metric tsdf|icp]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--metric tsdf|icp|fragopt]
 
 Metric (BASELINE.json, first half): depth frames/s integrated into a 512^3 TSDF (configs[1]: 1000 synthetic 640x480
 frames, rigid trajectory, 512^3 = 8^3 blocks of 64^3 voxels @ 3/512 m).  A "step" is one pass over that sequence:
@@ -19,6 +19,8 @@ frames, rigid trajectory, 512^3 = 8^3 blocks of 64^3 voxels @ 3/512 m).  A "step
   ctrlgrid      BASELINE configs[3]: the ControlGrid (nonrigid re-projection) mode on a 6 m room, pool of 4096 blocks
   icp           second half of the metric: fragment-pair ICP iterations/s (icp_bench.py); `--metric icp` prints it as
                 the line itself, and `--impl reference --metric icp` times the CPU port of that path
+  fragopt       the stage between the two halves: SLAC iterations of FragmentOptimizer over all
+                correspondences of the same 50 fragments (fragopt_bench.py); `--metric fragopt` / `--impl reference --metric fragopt`
 
 N > 1 (torchrun, one rank per GPU): ONE volume, its 64^3 blocks partitioned over the ranks ((xi+yi+zi) % N == rank,
 er_tsdf_set_partition); every rank sees every frame, no data-path collective during integration ("scaling":
@@ -193,6 +195,9 @@ def run_reference(args):
     if args.metric == "icp":
         import icp_bench
         return icp_bench.run_reference(args)
+    if args.metric == "fragopt":
+        import fragopt_bench
+        return fragopt_bench.run_reference(args)
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import pyoracle
     fps_step = args.ref_frames_per_step
@@ -395,7 +400,7 @@ def main():
     ap.add_argument("--steps", type=int, default=40)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--metric", default="tsdf", choices=["tsdf", "icp"],
+    ap.add_argument("--metric", default="tsdf", choices=["tsdf", "icp", "fragopt"],
                     help="which half of BASELINE.json's metric the printed line carries (the TSDF line always embeds `icp`)")
     ap.add_argument("--frames-per-step", type=int, default=SEQ_FRAMES,
                     help="frames handed to the library per call; must divide the 1000-frame sequence")
@@ -404,6 +409,10 @@ def main():
     ap.add_argument("--cpu-frames", type=int, default=120, help="frames timed for cpu_baseline (0 = skip)")
     ap.add_argument("--fusion", type=int, default=32, help="frames per fused launch triple (1..32)")
     ap.add_argument("--no-icp", action="store_true")
+    ap.add_argument("--no-fragopt", action="store_true")
+    ap.add_argument("--fragopt-fragments", type=int, default=50)
+    ap.add_argument("--fragopt-points", type=int, default=200000)
+    ap.add_argument("--fragopt-iterations", type=int, default=3)
     ap.add_argument("--no-ctr", action="store_true")
     ap.add_argument("--no-replica", action="store_true")
     ap.add_argument("--icp-fragments", type=int, default=50)
@@ -456,6 +465,19 @@ def main():
             os.write(real_stdout, (json.dumps(line) + "\n").encode())
         if world > 1:
             dist.destroy_process_group()
+        return 0
+
+    if args.metric == "fragopt":
+        import fragopt_bench
+        if world > 1:
+            if rank == 0:
+                os.write(real_stdout, (json.dumps({"metric": fragopt_bench.METRIC, "unavailable": "the FragmentOptimizer leg is single-GPU this round"}) + "\n").encode())
+            dist.destroy_process_group()
+            return 0
+        fo = fragopt_bench.run(local, fragments=args.fragopt_fragments, points=args.fragopt_points, iterations=args.fragopt_iterations,
+                               clock_sampler=ClockSampler)
+        sys.stdout.flush()
+        os.write(real_stdout, (json.dumps(fragopt_bench.as_line(fo, args, world)) + "\n").encode())
         return 0
 
     F = args.frames_per_step
@@ -683,6 +705,17 @@ def main():
         import icp_bench
         icp = icp_bench.run(local, rank, world, barrier, peak_gbs=peak, num_fragments=args.icp_fragments,
                             points=args.icp_points, clock_sampler=ClockSampler)
+    # ---------------- FragmentOptimizer --slac, single GPU; a failure here must not cost the line
+    fragopt = None
+    if not args.no_fragopt and world == 1:
+        try:
+            import fragopt_bench
+            torch.cuda.empty_cache()
+            fragopt = fragopt_bench.run(local, fragments=args.fragopt_fragments, points=args.fragopt_points,
+                                        iterations=args.fragopt_iterations, clock_sampler=ClockSampler)
+        except Exception as e:      # noqa: BLE001
+            fragopt = {"error": "%s: %s" % (type(e).__name__, e)}
+        torch.cuda.empty_cache()
     cpu = None
     if rank == 0 and world == 1 and args.cpu_frames > 0:
         cpu = cpu_baseline_leg(poses, args.cpu_frames)
@@ -700,7 +733,7 @@ def main():
                              "frames legitimately reuse their active blocks through L2" % (need * BYTES_PER_FRAME / 1e6)},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "wall_s_timed_region": wall, "blocks_owned_rank0": owned_blocks, "union_check": union, "replica": replica,
-            "ctrlgrid": ctr, "icp": icp,
+            "ctrlgrid": ctr, "icp": icp, "fragopt": fragopt,
         }
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())

@@ -107,15 +107,20 @@ def test_emulated_executable_matches_reference_binary(oracle, emul, golden, tmp_
 
 def test_emulated_kernels_against_the_oracle(emul, tmp_path):
     """API level: the emulated kernels (same header as the CUDA ones) against the numpy restatement."""
-    import fragopt_oracle as fo
     from elasticreconstruction_b200 import capi
+    api_check(lambda num: capi.FragOpt(num, 8, 3.0, library=emul["lib"]), tmp_path, vary_emulated_ctas=True)
+
+
+def api_check(make, tmp_path, vary_emulated_ctas=False):
+    """Shared with tests/test_fragopt_gpu.py: `make(num)` returns a capi.FragOpt on the library under test."""
+    import fragopt_oracle as fo
     d, _ = helpers.fragopt_case("three", str(tmp_path))
     xyzn, pairs, corres, ipose, _ = case_arrays("three", d)
     num = len(xyzn)
     L = fo.Lattice(8, 3.0)
     M = 6 * num + L.nper
     clouds = [fo.Cloud(L, c) for c in xyzn]
-    g = capi.FragOpt(num, 8, 3.0, library=emul["lib"])
+    g = make(num)
     for l in range(num):
         assert g.set_cloud(l, xyzn[l]) == len(xyzn[l])
     g.set_pairs(pairs, corres)
@@ -142,10 +147,10 @@ def test_emulated_kernels_against_the_oracle(emul, tmp_path):
     _, rows, flushes = g.assemble_stats()
     assert rows == sum(len(c) for c in corres) and 0 < flushes < rows / 8          # the sorted order keeps segments long
     # the split of the sorted list over CTAs does not matter
-    for ctas in ("1", "3", "64"):
+    for ctas in (("1", "3", "64") if vary_emulated_ctas else ()):
         os.environ["ER_FRAGOPT_EMUL_CTAS"] = ctas
         try:
-            g2 = capi.FragOpt(num, 8, 3.0, library=emul["lib"])
+            g2 = make(num)
         finally:
             del os.environ["ER_FRAGOPT_EMUL_CTAS"]
         for l in range(num):
@@ -198,3 +203,23 @@ def test_executable_help_and_missing_mode(emul, tmp_path):
     assert p.returncode == 0 and "--blasklist <blacklist_file>" in p.stdout and "--slac" in p.stdout
     p = subprocess.run([emul["exe"], "--num", "2"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=str(tmp_path))
     assert p.returncode == 2 and "not implemented" in p.stdout
+
+
+def test_bench_loop_on_the_emulated_library_matches_reference_binary(emul, golden, tmp_path):
+    """fragopt_bench.SlacLoop (the loop bench.py times, with its vectorised regulariser) over the emulated library."""
+    import importlib.util
+    from elasticreconstruction_b200 import capi
+    spec = importlib.util.spec_from_file_location("fragopt_bench", os.path.join(ROOT, "fragopt_bench.py"))
+    fb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fb)
+    d, _ = helpers.fragopt_case("three", str(tmp_path))
+    xyzn, pairs, corres, ipose, _ = case_arrays("three", d)
+    g = capi.FragOpt(len(xyzn), 8, 3.0, library=emul["lib"])
+    for l in range(len(xyzn)):
+        g.set_cloud(l, xyzn[l])
+    g.set_pairs(pairs, corres)
+    loop = fb.SlacLoop(g, ipose)
+    for _ in range(2):
+        loop.step()
+    assert np.abs(loop.pose - golden["three_slac_pose"]).max() <= POSE_TOL
+    assert np.abs(loop.expand().reshape(-1, 3) - golden["three_slac_ctr"]).max() <= CTR_TOL

@@ -1,0 +1,75 @@
+"""FragmentOptimizer path on the GPU (B200): the CUDA kernels of csrc/er_fragopt.cu through the C ABI against the numpy
+oracle (which is pinned against the verbatim reference binary, tests/test_fragopt_cpu.py), and the drop-in executable
+bin/FragmentOptimizer against the reference binary's pose.log / output.ctr (tests/golden/fragopt_golden.npz; live too
+where oracle/_ref/FragmentOptimizer_ref travelled to the box)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import helpers
+from test_fragopt_cpu import CTR_TOL, POSE_TOL, api_check, case_arrays
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EXE = os.path.join(ROOT, "elasticreconstruction_b200", "bin", "FragmentOptimizer")
+GOLDEN = os.path.join(ROOT, "tests", "golden", "fragopt_golden.npz")
+
+
+def test_kernels_against_the_oracle(tmp_path):
+    from elasticreconstruction_b200 import capi
+    api_check(lambda num: capi.FragOpt(num, 8, 3.0, device=0), tmp_path)
+
+
+@pytest.mark.parametrize("name", list(helpers.FRAGOPT_CASES))
+@pytest.mark.parametrize("mode", ["slac", "rigid"])
+def test_executable_matches_reference_binary(oracle, tmp_path, name, mode):
+    golden = np.load(GOLDEN)
+    d = str(tmp_path)
+    _, args = helpers.fragopt_case(name, d)
+    p = subprocess.run([EXE] + args + ["--" + mode, "--bench_json", os.path.join(d, "t.json")], cwd=d, stdout=subprocess.PIPE,
+                       stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert p.returncode == 0, p.stdout
+    pose = helpers.read_log_poses(os.path.join(d, "pose.log"))
+    ctr = np.loadtxt(os.path.join(d, "output.ctr"))
+    assert np.abs(pose - golden["%s_%s_pose" % (name, mode)]).max() <= POSE_TOL
+    assert np.abs(ctr - golden["%s_%s_ctr" % (name, mode)]).max() <= CTR_TOL
+    scores = [float(l.split(":")[1]) for l in p.stdout.splitlines() if "rror score is" in l]
+    assert np.allclose(scores, golden["%s_%s_scores" % (name, mode)], atol=0.0101)
+    if os.path.exists(oracle.REF_FRAGOPT):
+        os.rename(os.path.join(d, "pose.log"), os.path.join(d, "mine_pose.log"))
+        oracle.run_reference_fragopt(args + ["--" + mode], cwd=d)
+        assert np.abs(pose - helpers.read_log_poses(os.path.join(d, "pose.log"))).max() <= POSE_TOL
+        assert np.abs(ctr - np.loadtxt(os.path.join(d, "output.ctr"))).max() <= CTR_TOL
+
+
+def test_sample_file_and_sorted_order_independence(tmp_path):
+    """--write_xyzn_sample writes a readable binary_compressed PCD; two runs give the same poses to rounding (the flush
+    atomics are the only order-dependent step)."""
+    d = str(tmp_path)
+    _, args = helpers.fragopt_case("three", d)
+    outs = []
+    for k in range(2):
+        p = subprocess.run([EXE] + args + ["--slac", "--write_xyzn_sample", "50"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                           text=True, timeout=600)
+        assert p.returncode == 0, p.stdout
+        outs.append(helpers.read_log_poses(os.path.join(d, "pose.log")))
+    assert np.abs(outs[0] - outs[1]).max() <= 1e-8
+    raw = open(os.path.join(d, "sample.pcd"), "rb").read()
+    assert b"DATA binary_compressed\n" in raw
+    n = int([l for l in raw.split(b"\n") if l.startswith(b"POINTS")][0].split()[1])
+    body = raw[raw.index(b"DATA binary_compressed\n") + len(b"DATA binary_compressed\n"):]
+    csize, usize = np.frombuffer(body[:8], dtype="<u4")
+    assert usize == n * 32 and len(body) == 8 + csize and n > 100
+
+
+def test_no_correspondence_rows_outside_the_clouds():
+    from elasticreconstruction_b200 import capi
+    g = capi.FragOpt(2, 8, 3.0, device=0)
+    xyzn = np.array([[1, 1, 1, 0, 0, 1], [2, 2, 2, 0, 1, 0]], dtype=np.float32)
+    g.set_cloud(0, xyzn)
+    g.set_cloud(1, xyzn)
+    with pytest.raises(capi.ElasticError, match="outside their clouds"):
+        g.set_pairs([(0, 1)], [np.array([[0, 5]], dtype=np.int32)])
