@@ -64,7 +64,7 @@ __device__ __forceinline__ void load_point(const FoView& v, int g, int* base, fl
 
 __global__ void __launch_bounds__(kThreads, 3)
 slac_assemble_kernel(FoView v, const double* __restrict__ rot_t, double* JJ, double* Jb, double* score, unsigned long long* flushes) {
-  extern __shared__ double rows[];                 // [kThreads][kRowStride]
+  extern __shared__ __align__(16) double rows[];   // [kThreads][kRowStride]
   __shared__ SlacKey keys[kThreads];
   __shared__ int brk[kThreads];
   const int tid = threadIdx.x;
@@ -122,10 +122,10 @@ constexpr int kRigidSums = 91;
 __global__ void __launch_bounds__(kThreads)
 rigid_assemble_kernel(FoView v, const long long* __restrict__ pair_start, int chunks, double* out) {
   __shared__ double sums[kRigidSums];
-  const int pair = blockIdx.y;
+  const int pair = blockIdx.x;
   const long long b0 = pair_start[pair], b1 = pair_start[pair + 1];
   const long long n = b1 - b0;
-  const long long begin = b0 + n * (long long)blockIdx.x / chunks, end = b0 + n * (long long)(blockIdx.x + 1) / chunks;
+  const long long begin = b0 + n * (long long)blockIdx.y / chunks, end = b0 + n * (long long)(blockIdx.y + 1) / chunks;
   if (threadIdx.x < kRigidSums) sums[threadIdx.x] = 0.0;
   __syncthreads();
   double acc[kRigidSums];
@@ -645,7 +645,7 @@ int er_fragopt_rigid_assemble(er_fragopt* h, double* JJ, double* Jb, double* sco
   ER_CUDA(cudaMemsetAsync(h->d_rigid, 0, sums.size() * sizeof(double), h->stream));
   if (h->total) {
     const int chunks = (int)std::max<long long>(1, std::min<long long>(64, (4ll * h->sms + h->npairs - 1) / h->npairs));
-    rigid_assemble_kernel<<<dim3(chunks, h->npairs), kThreads, 0, h->stream>>>(view_of(h), h->d_pair_start, chunks, h->d_rigid);
+    rigid_assemble_kernel<<<dim3(h->npairs, chunks), kThreads, 0, h->stream>>>(view_of(h), h->d_pair_start, chunks, h->d_rigid);
     ++h->launches;
   }
   ER_CUDA(cudaMemcpyAsync(sums.data(), h->d_rigid, sums.size() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));

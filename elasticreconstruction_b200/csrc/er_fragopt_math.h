@@ -198,11 +198,16 @@ ER_FO_FN void fo_tile_of(int tid, int* ty, int* tx) {
   *tx = y + t;
 }
 
+struct alignas(16) D2 { double x, y; };
+
 // acc[16] += a (x) b for one staged row (tile threads) / acc[0..7] += b * row[8u..] (the eight vector threads)
 ER_FO_FN void fo_slac_mac(int tid, int ty, int tx, const double* row, double* acc) {
   if (tid < 120) {
-    const double a0 = row[4 * ty], a1 = row[4 * ty + 1], a2 = row[4 * ty + 2], a3 = row[4 * ty + 3];
-    const double b0 = row[4 * tx], b1 = row[4 * tx + 1], b2 = row[4 * tx + 2], b3 = row[4 * tx + 3];
+    // rows are 16-byte aligned and 4 * t doubles is a multiple of 32 bytes: four 128-bit shared-memory loads
+    const D2 p0 = *reinterpret_cast<const D2*>(row + 4 * ty), p1 = *reinterpret_cast<const D2*>(row + 4 * ty + 2);
+    const D2 q0 = *reinterpret_cast<const D2*>(row + 4 * tx), q1 = *reinterpret_cast<const D2*>(row + 4 * tx + 2);
+    const double a0 = p0.x, a1 = p0.y, a2 = p1.x, a3 = p1.y;
+    const double b0 = q0.x, b1 = q0.y, b2 = q1.x, b3 = q1.y;
     // fused multiply-adds: the order of the sums differs from the reference's anyway (per-pair dense matrices added
     // under an OpenMP critical section, OptApp.cpp:562-569), so only the tolerance matters here, and DFMA is the roof
     acc[0] = fma(a0, b0, acc[0]); acc[1] = fma(a0, b1, acc[1]); acc[2] = fma(a0, b2, acc[2]); acc[3] = fma(a0, b3, acc[3]);

@@ -18,3 +18,12 @@ if d.get("icp"):
     i = d["icp"]
     print("  icp %.0f pair-it/s passes %s e2e %.0f cpu %s" % (i["value"], i["passes_ms"], i["e2e"]["value"], (i.get("cpu_baseline") or {}).get("value")))
 print("  cpu_baseline:", (d.get("cpu_baseline") or {}).get("value"), "clocks", d.get("clocks"))
+if d.get("fragopt"):
+    f = d["fragopt"]
+    if "error" in f:
+        print("  fragopt ERROR:", f["error"])
+    else:
+        print("  fragopt %.3g corr/s, steps %s ms, kernel %.2f ms (%.3g rows/s, %.2f TFLOP/s fp64, frac %.3f), rows/flush %.0f, e2e %.3g, cpu %s, pose err %.2e (from %.2e)" % (
+            f["value"], f["steps_ms"], f["kernel"]["ms"], f["kernel"]["rows_per_s"], f["roofline"]["achieved"], f["roofline"]["frac"],
+            f["kernel"]["rows_per_flush"], f["e2e"]["value"], (f.get("cpu_baseline") or {}).get("value"), f["max_pose_error_vs_truth"],
+            f["initial_pose_error"]))
