@@ -61,7 +61,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
                     print(" ".join(cmd), flush=True)
                 subprocess.check_call(cmd)
             objs.append(o)
-        cmd = [_nvcc()] + ARCH + ["-shared", "-Xcompiler", "-fopenmp", "-o", LIB] + objs + ["-lcudart", "-lcusolver"]
+        cmd = [_nvcc()] + ARCH + ["-shared", "-Xcompiler", "-fopenmp", "-o", LIB] + objs + ["-lcudart", "-ldl"]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)

@@ -23,6 +23,7 @@
 //   ~100 bytes of gathers).
 #include <cub/device/device_radix_sort.cuh>
 #include <cusolverDn.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdint>
@@ -237,6 +238,42 @@ __global__ void add_upper_kernel(const double* __restrict__ base, const double* 
 
 }  // namespace
 
+// cuSOLVER (dense Cholesky of the SLAC system) is bound at the first er_fragopt_slac_solve, not at load time: the TSDF and
+// ICP paths, and every executable's start-up, do not pay for mapping cuSOLVER + cuBLAS.
+namespace {
+struct Solver {
+  void* dl = nullptr;
+  decltype(&cusolverDnCreate) create = nullptr;
+  decltype(&cusolverDnDestroy) destroy = nullptr;
+  decltype(&cusolverDnSetStream) set_stream = nullptr;
+  decltype(&cusolverDnDpotrf_bufferSize) potrf_buffer = nullptr;
+  decltype(&cusolverDnDpotrf) potrf = nullptr;
+  decltype(&cusolverDnDpotrs) potrs = nullptr;
+  bool ok = false;
+};
+Solver& solver_api() {
+  static Solver s;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    for (const char* name : {"libcusolver.so.11", "libcusolver.so", "/usr/local/cuda/lib64/libcusolver.so.11", "/usr/local/cuda/lib64/libcusolver.so"}) {
+      s.dl = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+      if (s.dl) break;
+    }
+    if (s.dl) {
+      s.create = (decltype(s.create))dlsym(s.dl, "cusolverDnCreate");
+      s.destroy = (decltype(s.destroy))dlsym(s.dl, "cusolverDnDestroy");
+      s.set_stream = (decltype(s.set_stream))dlsym(s.dl, "cusolverDnSetStream");
+      s.potrf_buffer = (decltype(s.potrf_buffer))dlsym(s.dl, "cusolverDnDpotrf_bufferSize");
+      s.potrf = (decltype(s.potrf))dlsym(s.dl, "cusolverDnDpotrf");
+      s.potrs = (decltype(s.potrs))dlsym(s.dl, "cusolverDnDpotrs");
+      s.ok = s.create && s.destroy && s.set_stream && s.potrf_buffer && s.potrf && s.potrs;
+    }
+  }
+  return s;
+}
+}  // namespace
+
 struct er_fragopt {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -357,7 +394,7 @@ void er_fragopt_destroy(er_fragopt* h) {
                   h->d_JJ, h->d_Jb, h->d_score, h->d_base, h->d_A, h->d_rhs, h->d_ctr, h->d_poses, h->d_rigid, h->d_flushes,
                   h->d_work, h->d_info};
   for (void* p : ptrs) if (p) cudaFree(p);
-  if (h->solver) cusolverDnDestroy(h->solver);
+  if (h->solver) solver_api().destroy(h->solver);
   for (int e = 0; e < 8; ++e) if (h->ev[e]) cudaEventDestroy(h->ev[e]);
   if (h->k0) cudaEventDestroy(h->k0);
   if (h->k1) cudaEventDestroy(h->k1);
@@ -603,13 +640,15 @@ int er_fragopt_slac_solve(er_fragopt* h, const double* base, const double* rhs, 
       return ER_ERR_CUDA;                                                                        \
     }                                                                                            \
   } while (0)
+  Solver& S = solver_api();
+  if (!S.ok) { er::set_error("er_fragopt_slac_solve: cannot load libcusolver (%s)", dlerror() ? dlerror() : "symbols missing"); return ER_ERR_CUDA; }
   if (!h->solver) {
-    ER_SOLVER(cusolverDnCreate(&h->solver));
-    ER_SOLVER(cusolverDnSetStream(h->solver, h->stream));
+    ER_SOLVER(S.create(&h->solver));
+    ER_SOLVER(S.set_stream(h->solver, h->stream));
   }
   // row-major upper == column-major lower
   int need = 0;
-  ER_SOLVER(cusolverDnDpotrf_bufferSize(h->solver, CUBLAS_FILL_MODE_LOWER, M, h->d_A, M, &need));
+  ER_SOLVER(S.potrf_buffer(h->solver, CUBLAS_FILL_MODE_LOWER, M, h->d_A, M, &need));
   if (need > h->work_len) {
     if (h->d_work) cudaFree(h->d_work);
     h->d_work = nullptr;
@@ -619,12 +658,12 @@ int er_fragopt_slac_solve(er_fragopt* h, const double* base, const double* rhs, 
   add_upper_kernel<<<dim3((M + 255) / 256, M), 256, 0, h->stream>>>(h->d_base, h->d_JJ, h->d_A, M);
   ++h->launches;
   ER_CUDA(cudaMemcpyAsync(h->d_rhs, rhs, sizeof(double) * M, cudaMemcpyHostToDevice, h->stream));
-  ER_SOLVER(cusolverDnDpotrf(h->solver, CUBLAS_FILL_MODE_LOWER, M, h->d_A, M, h->d_work, h->work_len, h->d_info));
+  ER_SOLVER(S.potrf(h->solver, CUBLAS_FILL_MODE_LOWER, M, h->d_A, M, h->d_work, h->work_len, h->d_info));
   int info = 0;
   ER_CUDA(cudaMemcpyAsync(&info, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
   ER_CUDA(cudaStreamSynchronize(h->stream));
   if (info != 0) { er::set_error("er_fragopt_slac_solve: the matrix is not positive definite (potrf info = %d)", info); return ER_ERR_ARG; }
-  ER_SOLVER(cusolverDnDpotrs(h->solver, CUBLAS_FILL_MODE_LOWER, M, 1, h->d_A, M, h->d_rhs, M, h->d_info));
+  ER_SOLVER(S.potrs(h->solver, CUBLAS_FILL_MODE_LOWER, M, 1, h->d_A, M, h->d_rhs, M, h->d_info));
   ER_CUDA(cudaMemcpyAsync(x, h->d_rhs, sizeof(double) * M, cudaMemcpyDeviceToHost, h->stream));
   ER_CUDA(cudaStreamSynchronize(h->stream));
   ER_CUDA(cudaGetLastError());

@@ -56,7 +56,7 @@ def test_sample_file_and_sorted_order_independence(tmp_path):
                            text=True, timeout=600)
         assert p.returncode == 0, p.stdout
         outs.append(helpers.read_log_poses(os.path.join(d, "pose.log")))
-    assert np.abs(outs[0] - outs[1]).max() <= 1e-8
+    assert np.abs(outs[0] - outs[1]).max() <= 2.5e-8          # one unit of the 8 printed decimals
     raw = open(os.path.join(d, "sample.pcd"), "rb").read()
     assert b"DATA binary_compressed\n" in raw
     n = int([l for l in raw.split(b"\n") if l.startswith(b"POINTS")][0].split()[1])
