@@ -5,8 +5,7 @@
 // the er_fragopt_* calls of include/elastic_b200.h; this file is the control flow of OptimizeSLAC / OptimizeRigid, the
 // lattice regulariser (one 3x3 polar rotation per lattice node) and the file formats.
 //
-// Modes: --slac (CVPR 2014) and --rigid.  --nonrigid (ICCV 2013; the reference's default when neither flag is given)
-// is not implemented in this build and says so.
+// Modes: --slac (CVPR 2014), --rigid and --nonrigid (ICCV 2013; the reference's default when neither flag is given).
 #include <omp.h>
 
 #include <algorithm>
@@ -631,6 +630,110 @@ struct App {
     if (!save_points(ctr)) { fprintf(stderr, "%s\n", er_last_error()); return 1; }
     return 0;
   }
+
+  // ---------------------------------------------------------------------------------------------- COptApp::OptimizeNonrigid
+  int optimize_nonrigid() {
+    fprintf(stderr, "Nonrigid optimization.\n");
+    printf("Parameters: weight %.5f, resolution %d, piece number %d, max iteration %d\n", o.weight, o.resolution, o.num, o.max_iteration);
+    if (!common_init(2)) return 1;
+    const size_t N = (size_t)num * nper;
+    std::vector<double> ctr(N, 0.0), ictr, oldctr, Ab(N);
+    if (o.init_ctr.length() > 1) {                            // COptApp::InitCtr
+      FILE* f = fopen(o.init_ctr.c_str(), "r");
+      if (f) {
+        char buf[1024];
+        for (size_t i = 0; i < N / 3; ++i) {
+          if (!fgets(buf, sizeof buf, f)) break;
+          sscanf(buf, "%lf %lf %lf", &ctr[i * 3], &ctr[i * 3 + 1], &ctr[i * 3 + 2]);
+        }
+        fclose(f);
+      }
+    } else {
+      pose = ipose;
+      pose.resize((size_t)num * 16);
+      pose_to_ctr(ctr);
+    }
+    ictr = ctr;
+    oldctr = ctr;
+    // COptApp::InitBaseAA: per fragment, every lattice edge visited from both ends adds [1 -1; -1 1] per axis; fragment 0's
+    // first node is pinned by three ones.  Upper triangle, as (row, col, value) triplets.
+    std::vector<int32_t> br, bc;
+    std::vector<double> bv;
+    for (int l = 0; l < num; ++l) {
+      for (int i = 0; i < r1; ++i)
+        for (int j = 0; j < r1; ++j)
+          for (int k = 0; k < r1; ++k) {
+            int nb[6], n;
+            neighbours(i, j, k, l * nper, nb, &n);
+            const int idx = node(i, j, k) * 3 + l * nper;
+            for (int t = 0; t < n; ++t)
+              for (int x = 0; x < 3; ++x) {
+                const int a = idx + x, b = nb[t] + x;
+                br.push_back(a); bc.push_back(a); bv.push_back(1.0);
+                br.push_back(b); bc.push_back(b); bv.push_back(1.0);
+                br.push_back(std::min(a, b)); bc.push_back(std::max(a, b)); bv.push_back(-1.0);
+              }
+          }
+      if (l == 0)
+        for (int x = 0; x < 3; ++x) { br.push_back(x); bc.push_back(x); bv.push_back(1.0); }
+    }
+    for (int itr = 0; itr < o.max_iteration; ++itr) {
+      double t0 = now_ms();
+      if (er_fragopt_update_normals(h, ctr.data()) != ER_OK) { fprintf(stderr, "%s\n", er_last_error()); return 1; }
+      t_update += now_ms() - t0;
+      t0 = now_ms();
+      printf("Processing %d ... ", npairs);
+      if (er_fragopt_nonrigid_assemble(h, o.weight) != ER_OK) { fprintf(stderr, "%s\n", er_last_error()); return 1; }
+      {
+        float ms = 0;
+        uint64_t r = 0, fl = 0;
+        if (er_fragopt_last_assemble_stats(h, &ms, &r, &fl) == ER_OK) { kernel_ms += ms; rows += r; flushes += fl; }
+      }
+      t_assemble += now_ms() - t0;
+      printf("Done.\n");
+      t0 = now_ms();
+      if (er_fragopt_nonrigid_factor(h, bv.size(), br.data(), bc.data(), bv.data()) != ER_OK) { fprintf(stderr, "%s\n", er_last_error()); return 1; }
+      t_solve += now_ms() - t0;
+      if (o.sample_num > 0) save_ctr(oldctr, "itr" + std::to_string(itr) + ".ctr");
+      for (int m = 0; m < o.max_inner_iteration; ++m) {
+        t0 = now_ms();
+        std::fill(Ab.begin(), Ab.end(), 0.0);
+#pragma omp parallel for schedule(static)
+        for (int l = 0; l < num; ++l)                          // fragments touch disjoint parts of Ab
+          for (int i = 0; i < r1; ++i)
+            for (int j = 0; j < r1; ++j)
+              for (int k = 0; k < r1; ++k) {
+                int nb[6], n;
+                neighbours(i, j, k, l * nper, nb, &n);
+                const int idx = node(i, j, k) * 3 + l * nper;
+                double R[9];
+                rotation_at(idx, nb, n, ictr, ctr, R);
+                for (int t = 0; t < n; ++t) {
+                  double d0[3];
+                  for (int x = 0; x < 3; ++x) d0[x] = ictr[idx + x] - ictr[nb[t] + x];
+                  for (int x = 0; x < 3; ++x) {
+                    const double bx = (R[3 * x] * d0[0] + R[3 * x + 1] * d0[1]) + R[3 * x + 2] * d0[2];
+                    Ab[idx + x] += bx;
+                    Ab[nb[t] + x] -= bx;
+                  }
+                }
+              }
+        t_reg += now_ms() - t0;
+        t0 = now_ms();
+        oldctr = ctr;
+        if (er_fragopt_nonrigid_solve(h, Ab.data(), ctr.data()) != ER_OK) { fprintf(stderr, "%s\n", er_last_error()); return 1; }
+        t_solve += now_ms() - t0;
+        double score = 0.0;
+        for (size_t e = 0; e < N; ++e) score += (oldctr[e] - ctr[e]) * (oldctr[e] - ctr[e]);
+        fprintf(stderr, "Iteration #%d:%d (%d:%d) : score is %.4f\n", itr + 1, m + 1, o.max_iteration, o.max_inner_iteration, sqrt(score));
+        if (o.sample_num > 0) save_ctr(ctr, "itr" + std::to_string(itr) + "_inner" + std::to_string(m) + "_out.ctr");
+      }
+      ++iterations_run;
+    }
+    save_ctr(ctr, o.ctr_file);
+    if (!save_points(ctr)) { fprintf(stderr, "%s\n", er_last_error()); return 1; }
+    return 0;
+  }
 };
 
 }  // namespace
@@ -676,12 +779,7 @@ int main(int argc, char** argv) {
   const char* mode;
   if (find_switch(argc, argv, "--slac")) { mode = "slac"; rc = app.optimize_slac(); }
   else if (find_switch(argc, argv, "--rigid")) { mode = "rigid"; rc = app.optimize_rigid(); }
-  else {
-    mode = "nonrigid";
-    fprintf(stderr, "Nonrigid optimization (the reference's default mode, OptApp.cpp:120-278) is not implemented in this build; "
-                    "use --slac or --rigid.\n");
-    rc = 2;
-  }
+  else { mode = "nonrigid"; rc = app.optimize_nonrigid(); }
   const double total = now_ms() - t0;
   fprintf(stderr, "Optimize All took %gms.\n", total);
   if (!o.bench_json.empty()) {

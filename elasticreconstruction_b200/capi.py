@@ -97,6 +97,10 @@ SIGNATURES = {
     "er_fragopt_slac_solve": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp]),
     "er_fragopt_slac_get_jj": (C.c_int, [C.c_void_p, c_dp]),
     "er_fragopt_rigid_assemble": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp]),
+    "er_fragopt_nonrigid_assemble": (C.c_int, [C.c_void_p, C.c_double]),
+    "er_fragopt_nonrigid_factor": (C.c_int, [C.c_void_p, C.c_size_t, c_i32p, c_i32p, c_dp]),
+    "er_fragopt_nonrigid_solve": (C.c_int, [C.c_void_p, c_dp, c_dp]),
+    "er_fragopt_nonrigid_get_aa": (C.c_int, [C.c_void_p, c_dp]),
     "er_fragopt_event_record": (C.c_int, [C.c_void_p, C.c_int]),
     "er_fragopt_event_elapsed_ms": (C.c_int, [C.c_void_p, C.c_int, C.c_int, c_fp]),
     "er_fragopt_launch_count": (C.c_uint64, [C.c_void_p]),
@@ -664,6 +668,28 @@ class FragOpt:
         score = C.c_double()
         self._check(self._L.er_fragopt_rigid_assemble(self._h, _dp(JJ), _dp(Jb), C.byref(score)))
         return JJ, Jb, score.value
+
+    def nonrigid_assemble(self, weight: float = 1.0):
+        self._check(self._L.er_fragopt_nonrigid_assemble(self._h, float(weight)))
+
+    def nonrigid_aa(self) -> np.ndarray:
+        n = self.num * self.nper
+        aa = np.empty((n, n), dtype=np.float64)
+        self._check(self._L.er_fragopt_nonrigid_get_aa(self._h, _dp(aa)))
+        return aa
+
+    def nonrigid_factor(self, rows, cols, vals):
+        r = np.ascontiguousarray(rows, dtype=np.int32)
+        c = np.ascontiguousarray(cols, dtype=np.int32)
+        v = np.ascontiguousarray(vals, dtype=np.float64)
+        self._check(self._L.er_fragopt_nonrigid_factor(self._h, len(v), r.ctypes.data_as(c_i32p), c.ctypes.data_as(c_i32p), _dp(v)))
+
+    def nonrigid_solve(self, rhs) -> np.ndarray:
+        n = self.num * self.nper
+        r = np.ascontiguousarray(rhs, dtype=np.float64).reshape(n)
+        x = np.empty(n, dtype=np.float64)
+        self._check(self._L.er_fragopt_nonrigid_solve(self._h, _dp(r), _dp(x)))
+        return x
 
     def assemble_stats(self):
         ms = C.c_float()

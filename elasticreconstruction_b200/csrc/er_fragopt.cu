@@ -37,6 +37,15 @@ using namespace er_fo;
 namespace {
 
 constexpr int kThreads = 128;
+// rows staged per batch (<= kThreads; 64 doubles of shared memory each) and resident CTAs per SM the kernel is compiled for
+#ifndef ER_FO_BATCH
+#define ER_FO_BATCH 128
+#endif
+#ifndef ER_FO_MINB
+#define ER_FO_MINB 3
+#endif
+constexpr int kBatch = ER_FO_BATCH;
+static_assert(kBatch <= kThreads && kBatch % 32 == 0, "ER_FO_BATCH");
 
 struct FoView {
   Lattice L;
@@ -63,11 +72,11 @@ __device__ __forceinline__ void load_point(const FoView& v, int g, int* base, fl
   p[0] = q.x; p[1] = q.y; p[2] = q.z;
 }
 
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, ER_FO_MINB)
 slac_assemble_kernel(FoView v, const double* __restrict__ rot_t, double* JJ, double* Jb, double* score, unsigned long long* flushes) {
-  extern __shared__ __align__(16) double rows[];   // [kThreads][kRowStride]
-  __shared__ SlacKey keys[kThreads];
-  __shared__ int brk[kThreads];
+  extern __shared__ __align__(16) double rows[];   // [kBatch][kRowStride]
+  __shared__ SlacKey keys[kBatch];
+  __shared__ int brk[kBatch];
   const int tid = threadIdx.x;
   int ty, tx;
   fo_tile_of(tid < 120 ? tid : 0, &ty, &tx);
@@ -78,8 +87,8 @@ slac_assemble_kernel(FoView v, const double* __restrict__ rot_t, double* JJ, dou
   for (int e = 0; e < 16; ++e) acc[e] = 0.0;
   SlacKey cur;
   cur.pair = -1; cur.bi = -1; cur.bj = -1;
-  for (long long base = begin; base < end; base += kThreads) {
-    const int cnt = (int)min((long long)kThreads, end - base);
+  for (long long base = begin; base < end; base += kBatch) {
+    const int cnt = (int)min((long long)kBatch, end - base);
     if (tid < cnt) {
       const int4 c = __ldg(&v.corr[base + tid]);
       int bi, bj;
@@ -115,6 +124,67 @@ slac_assemble_kernel(FoView v, const double* __restrict__ rot_t, double* JJ, dou
     fo_slac_flush(v.L, v.num, v.M, v.pair_i[cur.pair], v.pair_j[cur.pair], cur, tid, ty, tx, acc, JJ, Jb, score, DevAdd());
     if (tid == 0) atomicAdd(flushes, 1ull);
   }
+}
+
+// Nonrigid (OptApp.cpp:159-206): the same walk over the sorted list with 48-entry rows (24 unknowns of fragment i's
+// lattice, 24 of fragment j's) and no right-hand side; 96-thread CTAs, 78 threads own the 4x4 tiles of the 12 x 12-tile upper
+// triangle, rows are staged 96 at a time (36 KB of shared memory).  A = dense row-major N x N, N = num * nper.
+__global__ void __launch_bounds__(kNrThreads, 5)
+nonrigid_assemble_kernel(FoView v, double weight, long long N, double* A, unsigned long long* flushes) {
+  __shared__ __align__(16) double rows[kNrThreads * kNrStride];
+  __shared__ SlacKey keys[kNrThreads];
+  __shared__ int brk[kNrThreads];
+  const int tid = threadIdx.x;
+  int ty, tx;
+  fo_nr_tile_of(tid < kNrTiles ? tid : 0, &ty, &tx);
+  const long long begin = v.total * (long long)blockIdx.x / gridDim.x;
+  const long long end = v.total * (long long)(blockIdx.x + 1) / gridDim.x;
+  double acc[16];
+#pragma unroll
+  for (int e = 0; e < 16; ++e) acc[e] = 0.0;
+  SlacKey cur;
+  cur.pair = -1; cur.bi = -1; cur.bj = -1;
+  for (long long base = begin; base < end; base += kNrThreads) {
+    const int cnt = (int)min((long long)kNrThreads, end - base);
+    if (tid < cnt) {
+      const int4 c = __ldg(&v.corr[base + tid]);
+      const int4 a = __ldg(&v.statA[c.x]), b = __ldg(&v.statA[c.y]);
+      const float4 nn = v.nrm[c.x];
+      const float ri[3] = {__int_as_float(a.y), __int_as_float(a.z), __int_as_float(a.w)};
+      const float rj[3] = {__int_as_float(b.y), __int_as_float(b.z), __int_as_float(b.w)};
+      const float ni[3] = {nn.x, nn.y, nn.z};
+      fo_nonrigid_row(ri, ni, rj, weight, &rows[tid * kNrStride]);
+      SlacKey k;
+      k.pair = c.z; k.bi = a.x; k.bj = b.x;
+      keys[tid] = k;
+    }
+    __syncthreads();
+    if (tid < cnt) brk[tid] = !(keys[tid] == (tid == 0 ? cur : keys[tid - 1]));
+    __syncthreads();
+    for (int c = 0; c < cnt; ++c) {
+      if (brk[c]) {
+        if (cur.pair >= 0) {
+          fo_nr_flush(v.L, N, v.pair_i[cur.pair], v.pair_j[cur.pair], cur, tid, ty, tx, acc, A, DevAdd());
+          if (tid == 0) atomicAdd(flushes, 1ull);
+        }
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[e] = 0.0;
+        cur = keys[c];
+      }
+      if (tid < kNrTiles) fo_tile_mac<kNrStride>(ty, tx, &rows[c * kNrStride], acc);
+    }
+    __syncthreads();
+  }
+  if (cur.pair >= 0) {
+    fo_nr_flush(v.L, N, v.pair_i[cur.pair], v.pair_j[cur.pair], cur, tid, ty, tx, acc, A, DevAdd());
+    if (tid == 0) atomicAdd(flushes, 1ull);
+  }
+}
+
+__global__ void add_triplets_kernel(size_t nnz, const int* __restrict__ r, const int* __restrict__ c, const double* __restrict__ val, long long N,
+                                    double* A) {
+  const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (k < nnz) atomicAdd(&A[(long long)r[k] * N + c[k]], val[k]);
 }
 
 // Rigid: 12-entry rows; a CTA owns a range of one pair's correspondences, every thread sums its rows' products
@@ -298,6 +368,10 @@ struct er_fragopt {
   double* d_ctr = nullptr;
   float* d_poses = nullptr;
   double* d_rigid = nullptr;
+  double* d_AA = nullptr;            // nonrigid: dense N x N
+  double* d_nr_rhs = nullptr;
+  long long nr_N = 0;
+  bool nr_factored = false;
   unsigned long long* d_flushes = nullptr;
   bool have_base = false;
   cusolverDnHandle_t solver = nullptr;
@@ -377,7 +451,7 @@ er_fragopt* er_fragopt_create(int device, int num, int resolution, double length
   ok = ok && cudaMalloc(&h->d_flushes, sizeof(unsigned long long)) == cudaSuccess;
   ok = ok && cudaMalloc(&h->d_info, sizeof(int)) == cudaSuccess;
   if (ok) ok = cudaFuncSetAttribute(slac_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(kThreads * kRowStride * sizeof(double))) == cudaSuccess;
+                                    (int)(kBatch * kRowStride * sizeof(double))) == cudaSuccess;
   if (!ok) {
     er::set_error("er_fragopt_create: %s", cudaGetErrorString(cudaGetLastError()));
     er_fragopt_destroy(h);
@@ -392,7 +466,7 @@ void er_fragopt_destroy(er_fragopt* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->d_statA, h->d_statB, h->d_pos, h->d_nrm, h->d_pair_i, h->d_pair_j, h->d_pair_start, h->d_corr, h->d_rot,
                   h->d_JJ, h->d_Jb, h->d_score, h->d_base, h->d_A, h->d_rhs, h->d_ctr, h->d_poses, h->d_rigid, h->d_flushes,
-                  h->d_work, h->d_info};
+                  h->d_work, h->d_info, h->d_AA, h->d_nr_rhs};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->solver) solver_api().destroy(h->solver);
   for (int e = 0; e < 8; ++e) if (h->ev[e]) cudaEventDestroy(h->ev[e]);
@@ -597,9 +671,9 @@ int er_fragopt_slac_assemble(er_fragopt* h, const double* rot_t, double* Jb, dou
   ER_CUDA(cudaMemsetAsync(h->d_flushes, 0, sizeof(unsigned long long), h->stream));
   ER_CUDA(cudaEventRecord(h->k0, h->stream));
   if (h->total) {
-    const long long batches = (h->total + kThreads - 1) / kThreads;
-    const int grid = (int)std::min<long long>(batches, 3ll * h->sms);
-    slac_assemble_kernel<<<grid, kThreads, kThreads * kRowStride * sizeof(double), h->stream>>>(view_of(h), h->d_rot, h->d_JJ, h->d_Jb,
+    const long long batches = (h->total + kBatch - 1) / kBatch;
+    const int grid = (int)std::min<long long>(batches, (long long)ER_FO_MINB * h->sms);
+    slac_assemble_kernel<<<grid, kThreads, kBatch * kRowStride * sizeof(double), h->stream>>>(view_of(h), h->d_rot, h->d_JJ, h->d_Jb,
                                                                                                   h->d_score, h->d_flushes);
     ++h->launches;
   }
@@ -711,6 +785,129 @@ int er_fragopt_rigid_assemble(er_fragopt* h, double* JJ, double* Jb, double* sco
   return ER_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ nonrigid
+static int load_solver(er_fragopt* h, const char* who) {
+  Solver& S = solver_api();
+  if (!S.ok) { er::set_error("%s: cannot load libcusolver", who); return ER_ERR_CUDA; }
+  if (!h->solver) {
+    if (S.create(&h->solver) != CUSOLVER_STATUS_SUCCESS || S.set_stream(h->solver, h->stream) != CUSOLVER_STATUS_SUCCESS) {
+      er::set_error("%s: cusolverDnCreate failed", who);
+      return ER_ERR_CUDA;
+    }
+  }
+  return ER_OK;
+}
+
+int er_fragopt_nonrigid_assemble(er_fragopt* h, double weight) {
+  ER_ARG(h, "er_fragopt_nonrigid_assemble: null handle");
+  ER_ARG(h->d_corr || h->total == 0, "er_fragopt_nonrigid_assemble: call er_fragopt_set_pairs first");
+  ER_CUDA(cudaSetDevice(h->device));
+  const long long N = (long long)h->num * h->L.nper;
+  if (!h->d_AA) {
+    size_t free_b = 0, total_b = 0;
+    ER_CUDA(cudaMemGetInfo(&free_b, &total_b));
+    const double need = (double)N * (double)N * 8.0;
+    if (need > 0.9 * (double)free_b) {
+      er::set_error("er_fragopt_nonrigid_assemble: the dense %lld x %lld system needs %.1f GB, %.1f GB are free (use --slac for this many fragments)",
+                    N, N, need / 1e9, free_b / 1e9);
+      return ER_ERR_CAPACITY;
+    }
+    ER_CUDA(cudaMalloc(&h->d_AA, (size_t)N * (size_t)N * sizeof(double)));
+    ER_CUDA(cudaMalloc(&h->d_nr_rhs, (size_t)N * sizeof(double)));
+    h->nr_N = N;
+  }
+  ER_CUDA(cudaMemsetAsync(h->d_AA, 0, (size_t)N * (size_t)N * sizeof(double), h->stream));
+  ER_CUDA(cudaMemsetAsync(h->d_flushes, 0, sizeof(unsigned long long), h->stream));
+  ER_CUDA(cudaEventRecord(h->k0, h->stream));
+  if (h->total) {
+    const long long batches = (h->total + kNrThreads - 1) / kNrThreads;
+    const int grid = (int)std::min<long long>(batches, 5ll * h->sms);
+    nonrigid_assemble_kernel<<<grid, kNrThreads, 0, h->stream>>>(view_of(h), weight, N, h->d_AA, h->d_flushes);
+    ++h->launches;
+  }
+  ER_CUDA(cudaEventRecord(h->k1, h->stream));
+  h->last_rows = (uint64_t)h->total;
+  h->nr_factored = false;
+  ER_CUDA(cudaStreamSynchronize(h->stream));
+  ER_CUDA(cudaGetLastError());
+  return ER_OK;
+}
+
+int er_fragopt_nonrigid_get_aa(er_fragopt* h, double* aa) {
+  ER_ARG(h && aa && h->d_AA && !h->nr_factored, "er_fragopt_nonrigid_get_aa: assemble first (and before factoring)");
+  ER_CUDA(cudaSetDevice(h->device));
+  ER_CUDA(cudaMemcpyAsync(aa, h->d_AA, (size_t)h->nr_N * (size_t)h->nr_N * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  ER_CUDA(cudaStreamSynchronize(h->stream));
+  return ER_OK;
+}
+
+int er_fragopt_nonrigid_factor(er_fragopt* h, size_t nnz, const int32_t* rows, const int32_t* cols, const double* vals) {
+  ER_ARG(h && h->d_AA && !h->nr_factored, "er_fragopt_nonrigid_factor: assemble first");
+  ER_ARG(nnz == 0 || (rows && cols && vals), "er_fragopt_nonrigid_factor: bad arguments");
+  ER_CUDA(cudaSetDevice(h->device));
+  int rc = load_solver(h, "er_fragopt_nonrigid_factor");
+  if (rc != ER_OK) return rc;
+  const long long N = h->nr_N;
+  ER_ARG(N < (1ll << 31), "er_fragopt_nonrigid_factor: system too large for cuSOLVER's 32-bit interface");
+  for (size_t k = 0; k < nnz; ++k)
+    ER_ARG(rows[k] >= 0 && rows[k] <= cols[k] && cols[k] < N, "er_fragopt_nonrigid_factor: triplets must lie in the upper triangle");
+  if (nnz) {
+    int *d_r = nullptr, *d_c = nullptr;
+    double* d_v = nullptr;
+    cudaError_t e = cudaMalloc(&d_r, nnz * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&d_c, nnz * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc(&d_v, nnz * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_r, rows, nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_c, cols, nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_v, vals, nnz * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) {
+      add_triplets_kernel<<<(unsigned)((nnz + 255) / 256), 256, 0, h->stream>>>(nnz, d_r, d_c, d_v, N, h->d_AA);
+      ++h->launches;
+      e = cudaStreamSynchronize(h->stream);
+    }
+    for (void* p : {(void*)d_r, (void*)d_c, (void*)d_v}) if (p) cudaFree(p);
+    if (e != cudaSuccess) { er::set_error("er_fragopt_nonrigid_factor: %s", cudaGetErrorString(e)); return ER_ERR_CUDA; }
+  }
+  Solver& S = solver_api();
+  int need = 0;
+  if (S.potrf_buffer(h->solver, CUBLAS_FILL_MODE_LOWER, (int)N, h->d_AA, (int)N, &need) != CUSOLVER_STATUS_SUCCESS) {
+    er::set_error("er_fragopt_nonrigid_factor: potrf_bufferSize failed");
+    return ER_ERR_CUDA;
+  }
+  if (need > h->work_len) {
+    if (h->d_work) cudaFree(h->d_work);
+    h->d_work = nullptr;
+    ER_CUDA(cudaMalloc(&h->d_work, sizeof(double) * (size_t)need));
+    h->work_len = need;
+  }
+  if (S.potrf(h->solver, CUBLAS_FILL_MODE_LOWER, (int)N, h->d_AA, (int)N, h->d_work, h->work_len, h->d_info) != CUSOLVER_STATUS_SUCCESS) {
+    er::set_error("er_fragopt_nonrigid_factor: potrf failed");
+    return ER_ERR_CUDA;
+  }
+  int info = 0;
+  ER_CUDA(cudaMemcpyAsync(&info, h->d_info, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  ER_CUDA(cudaStreamSynchronize(h->stream));
+  if (info != 0) { er::set_error("er_fragopt_nonrigid_factor: the matrix is not positive definite (potrf info = %d)", info); return ER_ERR_ARG; }
+  h->nr_factored = true;
+  return ER_OK;
+}
+
+int er_fragopt_nonrigid_solve(er_fragopt* h, const double* rhs, double* x) {
+  ER_ARG(h && rhs && x && h->nr_factored, "er_fragopt_nonrigid_solve: factor first");
+  ER_CUDA(cudaSetDevice(h->device));
+  const long long N = h->nr_N;
+  Solver& S = solver_api();
+  ER_CUDA(cudaMemcpyAsync(h->d_nr_rhs, rhs, sizeof(double) * (size_t)N, cudaMemcpyHostToDevice, h->stream));
+  if (S.potrs(h->solver, CUBLAS_FILL_MODE_LOWER, (int)N, 1, h->d_AA, (int)N, h->d_nr_rhs, (int)N, h->d_info) != CUSOLVER_STATUS_SUCCESS) {
+    er::set_error("er_fragopt_nonrigid_solve: potrs failed");
+    return ER_ERR_CUDA;
+  }
+  ER_CUDA(cudaMemcpyAsync(x, h->d_nr_rhs, sizeof(double) * (size_t)N, cudaMemcpyDeviceToHost, h->stream));
+  ER_CUDA(cudaStreamSynchronize(h->stream));
+  ER_CUDA(cudaGetLastError());
+  return ER_OK;
+}
+
 int er_fragopt_event_record(er_fragopt* h, int slot) {
   ER_ARG(h && slot >= 0 && slot < 8, "er_fragopt_event_record: bad slot");
   ER_CUDA(cudaSetDevice(h->device));
@@ -736,7 +933,7 @@ int er_fragopt_sync(er_fragopt* h) {
 }
 
 int er_fragopt_last_assemble_stats(er_fragopt* h, float* kernel_ms, uint64_t* rows, uint64_t* flushes) {
-  ER_ARG(h && h->d_JJ, "er_fragopt_last_assemble_stats: nothing assembled yet");
+  ER_ARG(h && (h->d_JJ || h->d_AA), "er_fragopt_last_assemble_stats: nothing assembled yet");
   ER_CUDA(cudaSetDevice(h->device));
   if (kernel_ms) {
     ER_CUDA(cudaEventSynchronize(h->k1));

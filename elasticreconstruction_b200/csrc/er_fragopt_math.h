@@ -13,7 +13,7 @@
 //   fo_slac_row            one row of the SLAC Jacobian        OptApp.cpp:487-545
 //   fo_slac_flush_*        its normal-equation update          OptApp.cpp:547-559
 //   fo_rigid_row           one row of the rigid Jacobian       OptApp.cpp:332-369
-//   fo_nonrigid_row        one row of the nonrigid system      OptApp.cpp:171-190
+//   fo_nonrigid_row / fo_nr_flush   one row of the nonrigid system and its update   OptApp.cpp:171-195
 #pragma once
 
 #include <cmath>
@@ -141,10 +141,29 @@ ER_FO_FN void fo_update_pose(const float m[16], float p[3], float n[3]) {
 // ------------------------------------------------------------------------------------------------ SLAC
 // One correspondence (pi in fragment i, pj in fragment j) gives a Jacobian row with 60 entries
 //   [ 6 pose i | 6 pose j | 8 corners x 3 of pi's lattice cell | 8 x 3 of pj's ]   (OptApp.cpp:500-545)
-// and the residual b.  row[60] receives b, row[61..63] zeros (the kernel's shared-memory rows are 64 doubles).
+// and the residual b.  Element 60 receives b, 61..63 zeros (the kernel's shared-memory rows are 64 doubles; fo_pos maps
+// element numbers to positions).
 // rot_ti / rot_tj = pose_rot_t_[i], [j] row-major.
 constexpr int kSlacRow = 60;
 constexpr int kRowStride = 64;
+
+// Where element e of a staged row lives in shared memory.  A thread of the accumulation loop needs the four values
+// 4t .. 4t+3 of two tile indices t; with the natural order (e -> e) neighbouring tiles are 32 bytes apart and the 16-byte
+// loads of a quarter-warp hit every bank twice (measured: 53 % of the kernel's shared-memory wavefronts were bank conflicts,
+// the shared-memory pipe busy 84 % of the cycles, profiles/r2_slac_assemble_kernel_v1.txt).  Two planes instead: plane 0 holds the
+// pairs (4t, 4t+1) of all tiles back to back, plane 1 the pairs (4t+2, 4t+3), so that consecutive tiles are consecutive
+// 16-byte words and a quarter-warp reads one conflict-free 128-byte line.
+#ifndef ER_FO_PLANES
+#define ER_FO_PLANES 1
+#endif
+template <int STRIDE>
+ER_FO_FN int fo_pos(int e) {
+#if ER_FO_PLANES
+  return ((e >> 1) & 1) * (STRIDE / 2) + (e >> 2) * 2 + (e & 1);
+#else
+  return e;
+#endif
+}
 
 ER_FO_FN void fo_slac_row(const float pi[3], const float ni[3], const float ri[3], const float pj[3], const float rj[3],
                           const double* rot_ti, const double* rot_tj, double* row) {
@@ -154,8 +173,11 @@ ER_FO_FN void fo_slac_row(const float pi[3], const float ni[3], const float ri[3
   const double t0 = ppj[1] * npi[2] - ppj[2] * npi[1];       // ppj.cross(npi)
   const double t1 = ppj[2] * npi[0] - ppj[0] * npi[2];
   const double t2 = ppj[0] * npi[1] - ppj[1] * npi[0];
-  row[0] = t0; row[1] = t1; row[2] = t2; row[3] = npi[0]; row[4] = npi[1]; row[5] = npi[2];
-  row[6] = -t0; row[7] = -t1; row[8] = -t2; row[9] = -npi[0]; row[10] = -npi[1]; row[11] = -npi[2];
+  constexpr int S = kRowStride;
+  row[fo_pos<S>(0)] = t0; row[fo_pos<S>(1)] = t1; row[fo_pos<S>(2)] = t2;
+  row[fo_pos<S>(3)] = npi[0]; row[fo_pos<S>(4)] = npi[1]; row[fo_pos<S>(5)] = npi[2];
+  row[fo_pos<S>(6)] = -t0; row[fo_pos<S>(7)] = -t1; row[fo_pos<S>(8)] = -t2;
+  row[fo_pos<S>(9)] = -npi[0]; row[fo_pos<S>(10)] = -npi[1]; row[fo_pos<S>(11)] = -npi[2];
   double dTi[3], dTj[3];
   for (int r = 0; r < 3; ++r) {
     dTi[r] = (rot_ti[3 * r] * npi[0] + rot_ti[3 * r + 1] * npi[1]) + rot_ti[3 * r + 2] * npi[2];
@@ -166,11 +188,11 @@ ER_FO_FN void fo_slac_row(const float pi[3], const float ni[3], const float ri[3
   fo_vals(rj, c);
   for (int ll = 0; ll < 8; ++ll)
     for (int xyz = 0; xyz < 3; ++xyz) {
-      row[12 + ll * 3 + xyz] = a[ll] * dTi[xyz];
-      row[36 + ll * 3 + xyz] = c[ll] * dTj[xyz];
+      row[fo_pos<S>(12 + ll * 3 + xyz)] = a[ll] * dTi[xyz];
+      row[fo_pos<S>(36 + ll * 3 + xyz)] = c[ll] * dTj[xyz];
     }
-  row[60] = b;
-  row[61] = 0.0; row[62] = 0.0; row[63] = 0.0;
+  row[fo_pos<S>(60)] = b;
+  row[fo_pos<S>(61)] = 0.0; row[fo_pos<S>(62)] = 0.0; row[fo_pos<S>(63)] = 0.0;
 }
 
 // The segment key: all correspondences with the same key share the 60 global column indices of their rows.
@@ -200,24 +222,35 @@ ER_FO_FN void fo_tile_of(int tid, int* ty, int* tx) {
 
 struct alignas(16) D2 { double x, y; };
 
-// acc[16] += a (x) b for one staged row (tile threads) / acc[0..7] += b * row[8u..] (the eight vector threads)
+// acc[16] += a (x) b for the 4x4 tile (ty, tx) of row^T row
+template <int STRIDE>
+ER_FO_FN void fo_tile_mac(int ty, int tx, const double* row, double* acc) {
+  // four 128-bit shared-memory loads (rows are 16-byte aligned)
+#if ER_FO_PLANES
+  const D2 p0 = *reinterpret_cast<const D2*>(row + 2 * ty), p1 = *reinterpret_cast<const D2*>(row + STRIDE / 2 + 2 * ty);
+  const D2 q0 = *reinterpret_cast<const D2*>(row + 2 * tx), q1 = *reinterpret_cast<const D2*>(row + STRIDE / 2 + 2 * tx);
+#else
+  const D2 p0 = *reinterpret_cast<const D2*>(row + 4 * ty), p1 = *reinterpret_cast<const D2*>(row + 4 * ty + 2);
+  const D2 q0 = *reinterpret_cast<const D2*>(row + 4 * tx), q1 = *reinterpret_cast<const D2*>(row + 4 * tx + 2);
+#endif
+  const double a0 = p0.x, a1 = p0.y, a2 = p1.x, a3 = p1.y;
+  const double b0 = q0.x, b1 = q0.y, b2 = q1.x, b3 = q1.y;
+  // fused multiply-adds: the order of the sums differs from the reference's anyway (per-pair dense matrices added
+  // under an OpenMP critical section, OptApp.cpp:562-569), so only the tolerance matters here, and DFMA is the roof
+  acc[0] = fma(a0, b0, acc[0]); acc[1] = fma(a0, b1, acc[1]); acc[2] = fma(a0, b2, acc[2]); acc[3] = fma(a0, b3, acc[3]);
+  acc[4] = fma(a1, b0, acc[4]); acc[5] = fma(a1, b1, acc[5]); acc[6] = fma(a1, b2, acc[6]); acc[7] = fma(a1, b3, acc[7]);
+  acc[8] = fma(a2, b0, acc[8]); acc[9] = fma(a2, b1, acc[9]); acc[10] = fma(a2, b2, acc[10]); acc[11] = fma(a2, b3, acc[11]);
+  acc[12] = fma(a3, b0, acc[12]); acc[13] = fma(a3, b1, acc[13]); acc[14] = fma(a3, b2, acc[14]); acc[15] = fma(a3, b3, acc[15]);
+}
+
+// one staged row: the tile threads add their tile, the eight vector threads acc[0..7] += b * row[8u..]
 ER_FO_FN void fo_slac_mac(int tid, int ty, int tx, const double* row, double* acc) {
   if (tid < 120) {
-    // rows are 16-byte aligned and 4 * t doubles is a multiple of 32 bytes: four 128-bit shared-memory loads
-    const D2 p0 = *reinterpret_cast<const D2*>(row + 4 * ty), p1 = *reinterpret_cast<const D2*>(row + 4 * ty + 2);
-    const D2 q0 = *reinterpret_cast<const D2*>(row + 4 * tx), q1 = *reinterpret_cast<const D2*>(row + 4 * tx + 2);
-    const double a0 = p0.x, a1 = p0.y, a2 = p1.x, a3 = p1.y;
-    const double b0 = q0.x, b1 = q0.y, b2 = q1.x, b3 = q1.y;
-    // fused multiply-adds: the order of the sums differs from the reference's anyway (per-pair dense matrices added
-    // under an OpenMP critical section, OptApp.cpp:562-569), so only the tolerance matters here, and DFMA is the roof
-    acc[0] = fma(a0, b0, acc[0]); acc[1] = fma(a0, b1, acc[1]); acc[2] = fma(a0, b2, acc[2]); acc[3] = fma(a0, b3, acc[3]);
-    acc[4] = fma(a1, b0, acc[4]); acc[5] = fma(a1, b1, acc[5]); acc[6] = fma(a1, b2, acc[6]); acc[7] = fma(a1, b3, acc[7]);
-    acc[8] = fma(a2, b0, acc[8]); acc[9] = fma(a2, b1, acc[9]); acc[10] = fma(a2, b2, acc[10]); acc[11] = fma(a2, b3, acc[11]);
-    acc[12] = fma(a3, b0, acc[12]); acc[13] = fma(a3, b1, acc[13]); acc[14] = fma(a3, b2, acc[14]); acc[15] = fma(a3, b3, acc[15]);
+    fo_tile_mac<kRowStride>(ty, tx, row, acc);
   } else {
-    const double b = row[60];
+    const double b = row[fo_pos<kRowStride>(60)];
     const int u = tid - 120;
-    for (int e = 0; e < 8; ++e) acc[e] = fma(b, row[8 * u + e], acc[e]);
+    for (int e = 0; e < 8; ++e) acc[e] = fma(b, row[fo_pos<kRowStride>(8 * u + e)], acc[e]);
   }
 }
 
@@ -275,16 +308,65 @@ ER_FO_FN void fo_rigid_row(const float pi[3], const float ni[3], const float pj[
 }
 
 // ------------------------------------------------------------------------------------------------ nonrigid
-// OptApp.cpp:177-190: 24 entries on fragment i's lattice (corner ll, axis t -> position t*8 + ll) and 24 on j's;
-// val1 = pi.val * weight * n_i[t], val2 = -pj.val * weight * n_i[t] with float val, double weight, float normal.
-ER_FO_FN void fo_nonrigid_row(const float ri[3], const float ni[3], const float rj[3], double weight, double v1[24], double v2[24]) {
+// OptApp.cpp:171-195.  One correspondence gives a 48-entry row [24 on fragment i's lattice | 24 on fragment j's]:
+// position t*8 + ll (axis t, corner ll) holds pi.val_[ll] * weight * pi.n_[t], position 24 + t*8 + ll holds
+// -pj.val_[ll] * weight * pi.n_[t] (float val, double weight, float normal), at the unknowns idx_[ll] + t of the two
+// fragments' lattices.  The system has no data right-hand side: mati / matj / matij add row^T row only.
+constexpr int kNrRow = 48;
+constexpr int kNrStride = 48;
+constexpr int kNrThreads = 96;     // 78 of them own a 4x4 tile of the 12 x 12-tile upper triangle
+constexpr int kNrTiles = 78;
+
+ER_FO_FN void fo_nonrigid_row(const float ri[3], const float ni[3], const float rj[3], double weight, double* row) {
   float a[8], c[8];
   fo_vals(ri, a);
   fo_vals(rj, c);
   for (int t = 0; t < 3; ++t)
     for (int ll = 0; ll < 8; ++ll) {
-      v1[t * 8 + ll] = a[ll] * weight * ni[t];
-      v2[t * 8 + ll] = -c[ll] * weight * ni[t];
+      row[fo_pos<kNrStride>(t * 8 + ll)] = a[ll] * weight * ni[t];
+      row[fo_pos<kNrStride>(24 + t * 8 + ll)] = -c[ll] * weight * ni[t];
+    }
+}
+
+ER_FO_FN void fo_nr_tile_of(int tid, int* ty, int* tx) {
+  int t = tid, y = 0;
+  while (t >= 12 - y) { t -= 12 - y; ++y; }
+  *ty = y;
+  *tx = y + t;
+}
+
+// unknown of row position q (0..47): fragment i's / j's lattice block, node of the cell's corner ll, axis t
+ER_FO_FN long long fo_nr_index(const Lattice& L, int i, int j, int bi, int bj, int q) {
+  const int half = q < 24 ? 0 : 1, r = q - 24 * half, t = r / 8, ll = r % 8;
+  return (long long)(half ? j : i) * L.nper + (long long)((half ? bj : bi) + fo_corner_offset(L, ll)) * 3 + t;
+}
+
+// A (dense, row-major N x N, N = num * nper) += the segment's tile, upper triangle only: the reference's solver reads
+// thisAA.selfadjointView<Upper>() (OptApp.cpp:209-211), so of mati / matj (full symmetric blocks) the upper halves
+// count, and matij -- rows of fragment i, columns of fragment j, never its transpose (OptApp.cpp:194) -- counts only
+// when i < j: for a pair listed with idx0 > idx1 the cross term lies in the lower triangle and is never read.
+template <class Add>
+ER_FO_FN void fo_nr_flush(const Lattice& L, long long N, int i, int j, const SlacKey& key, int tid, int ty, int tx, const double* acc,
+                          double* A, Add ADD) {
+  if (tid >= kNrTiles) return;
+  long long gp[4], gq[4];
+  for (int r = 0; r < 4; ++r) {
+    gp[r] = fo_nr_index(L, i, j, key.bi, key.bj, 4 * ty + r);
+    gq[r] = fo_nr_index(L, i, j, key.bi, key.bj, 4 * tx + r);
+  }
+  for (int r = 0; r < 4; ++r)
+    for (int s = 0; s < 4; ++s) {
+      const int p = 4 * ty + r, q = 4 * tx + s;
+      if (p > q) continue;
+      const bool cross = (p < 24) != (q < 24);
+      if (cross && !(i < j)) continue;
+      const double v = acc[4 * r + s];
+      if (v == 0.0) continue;
+      const long long a = gp[r], b = gq[s];
+      if (p == q) ADD(&A[a * N + a], v);
+      else if (a == b) ADD(&A[a * N + a], 2 * v);
+      else if (a < b) ADD(&A[a * N + b], v);
+      else ADD(&A[b * N + a], v);
     }
 }
 

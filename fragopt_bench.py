@@ -293,3 +293,54 @@ def run_reference(args):
                       "e2e": {"value": v, "unit": "correspondences/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                       "gpu_launches": 0}), flush=True)
     return 0
+
+
+def base_aa_triplets(num):
+    """COptApp::InitBaseAA (OptApp.cpp:765-811) as upper-triangle triplets: per fragment the lattice graph Laplacian, every edge
+    visited from both ends; fragment 0's first node pinned."""
+    nb = neighbour_table()
+    nper = 3 * len(nb)
+    u, t = np.nonzero(nb >= 0)
+    v = nb[u, t]
+    rows, cols, vals = [], [], []
+    for l in range(num):
+        for x in range(3):
+            a, b = l * nper + 3 * u + x, l * nper + 3 * v + x
+            rows += [a, b, np.minimum(a, b)]
+            cols += [a, b, np.maximum(a, b)]
+            vals += [np.ones(len(a)), np.ones(len(a)), -np.ones(len(a))]
+    rows.append(np.arange(3)); cols.append(np.arange(3)); vals.append(np.ones(3))
+    return np.concatenate(rows).astype(np.int32), np.concatenate(cols).astype(np.int32), np.concatenate(vals)
+
+
+def nonrigid_probe(local: int, fragments: int = 8, points: int = 50_000, weight: float = 1.0):
+    """One outer iteration of OptimizeNonrigid at a size whose dense system fits comfortably: assembly kernel, factorisation, one solve."""
+    frags = [synth.make_local_fragment(i, points) for i in range(fragments)]
+    pairs = [(i, j) for i in range(fragments) for j in range(i + 1, fragments)]
+    corres = device_correspondences(frags, pairs, local)
+    rows = int(sum(len(c) for c in corres))
+    g = capi.FragOpt(fragments, RES, LENGTH, device=local)
+    for l in range(fragments):
+        g.set_cloud(l, np.concatenate([frags[l][0], frags[l][1]], axis=1))
+    g.set_pairs(pairs, corres)
+    ipose = np.array([synth.fragopt_initial_pose(i) for i in range(fragments)])
+    ijk, unit = lattice_nodes()
+    lat = ijk * unit
+    ctr = np.concatenate([lat @ ipose[l][:3, :3].T + ipose[l][:3, 3] for l in range(fragments)]).reshape(-1)
+    g.update_normals(ctr)
+    r, c, v = base_aa_triplets(fragments)
+    out = {"fragments": fragments, "rows": rows, "unknowns": fragments * g.nper, "dense_gb": (fragments * g.nper) ** 2 * 8 / 1e9}
+    for rep in range(2):
+        t0 = time.perf_counter()
+        g.nonrigid_assemble(weight)
+        t1 = time.perf_counter()
+        ms, _, flushes = g.assemble_stats()
+        g.nonrigid_factor(r, c, v)
+        t2 = time.perf_counter()
+        x = g.nonrigid_solve(np.cos(np.arange(fragments * g.nper) * 0.01))
+        t3 = time.perf_counter()
+        out["rep%d" % rep] = {"assemble_kernel_ms": ms, "assemble_call_ms": (t1 - t0) * 1e3, "factor_ms": (t2 - t1) * 1e3, "solve_ms": (t3 - t2) * 1e3,
+                              "flushes": int(flushes), "rows_per_s": rows / (ms * 1e-3),
+                              "fp64_tflops": 2.0 * (48 * 49 // 2) * rows / (ms * 1e-3) / 1e12, "x_finite": bool(np.isfinite(x).all())}
+    g.close()
+    return out

@@ -286,9 +286,20 @@ int er_fragopt_slac_get_jj(er_fragopt* h, double* jj);
  * OptApp.cpp:323-325, are the caller's.) */
 int er_fragopt_rigid_assemble(er_fragopt* h, double* JJ, double* Jb, double* score);
 
-/* Data term of one nonrigid outer iteration (OptApp.cpp:159-206) as dense 3*8 x 3*8 blocks is not what the
- * reference stores; it is delivered in coordinate form instead: for every (pair, cell, cell) segment the 24x24
- * blocks ii, jj, ij.  Not implemented in this round. */
+/* Nonrigid mode (COptApp::OptimizeNonrigid, OptApp.cpp:120-278; unknowns = num * nper lattice coordinates).  The system
+ * is kept DENSE on the device (row-major N x N doubles, N = num * nper, upper triangle; 344 MB for 3 fragments, 3.8 GB
+ * for 10, 96 GB for 50 -- ER_ERR_CAPACITY when it does not fit) and factorised by cuSOLVER where the reference calls
+ * CholmodSupernodalLLT on a sparse matrix.
+ *   assemble  the pair loop (OptApp.cpp:159-206): sum of row^T row over all correspondences, rows of 48 entries
+ *             (pi.val * weight * n_i on fragment i's lattice, -pj.val * weight * n_i on fragment j's); call
+ *             er_fragopt_update_normals first (OptApp.cpp:151-153)
+ *   factor    thisAA = data + baseAA (given as upper-triangle triplets), then the Cholesky factorisation (OptApp.cpp:155,209-211)
+ *   solve     ctr = solver.solve(Ab) (OptApp.cpp:262), any number of times per factorisation */
+int er_fragopt_nonrigid_assemble(er_fragopt* h, double weight);
+int er_fragopt_nonrigid_factor(er_fragopt* h, size_t nnz, const int32_t* rows, const int32_t* cols, const double* vals);
+int er_fragopt_nonrigid_solve(er_fragopt* h, const double* rhs, double* x);
+/* The assembled data term (N*N doubles, upper triangle), valid between assemble and factor (tests). */
+int er_fragopt_nonrigid_get_aa(er_fragopt* h, double* aa);
 
 /* Timing / accounting like the other paths (events on the handle's stream). */
 int er_fragopt_event_record(er_fragopt* h, int slot);

@@ -374,3 +374,108 @@ def optimize_rigid(xyzn, pairs, corres, ipose, resolution=8, length=3.0, iterati
     lat = np.array([[i * L.unit_d, j * L.unit_d, k * L.unit_d] for k in range(L.r1) for j in range(L.r1) for i in range(L.r1)])
     ctr = np.concatenate([lat @ pose[l][:3, :3].T + pose[l][:3, 3] for l in range(num)])
     return pose, ctr
+
+
+# ------------------------------------------------------------------------------------------------------------ nonrigid
+def nonrigid_rows(ci: Cloud, cj: Cloud, rows, weight):
+    """OptApp.cpp:177-190: idx1/val1 on fragment i's lattice block, idx2/val2 on fragment j's (24 entries each)."""
+    ii, jj = rows[:, 0], rows[:, 1]
+    n = len(rows)
+    idx1 = np.empty((n, 24), dtype=np.int64)
+    idx2 = np.empty((n, 24), dtype=np.int64)
+    v1 = np.empty((n, 24))
+    v2 = np.empty((n, 24))
+    ni = ci.n[ii].astype(np.float64)
+    for t in range(3):
+        for ll in range(8):
+            idx1[:, t * 8 + ll] = ci.idx[ii, ll] + t
+            idx2[:, t * 8 + ll] = cj.idx[jj, ll] + t
+            v1[:, t * 8 + ll] = ci.val[ii, ll].astype(np.float64) * weight * ni[:, t]
+            v2[:, t * 8 + ll] = -cj.val[jj, ll].astype(np.float64) * weight * ni[:, t]
+    return idx1, v1, idx2, v2
+
+
+def nonrigid_data_matrix(clouds, pairs, corres, nper, weight, chunk=2048):
+    """Sum of mati + matj + matij over all pairs (OptApp.cpp:159-206), as the solver sees it: the upper triangle.  matij
+    (rows of fragment i, columns of fragment j) lies in the upper triangle only when i < j."""
+    num = len(clouds)
+    N = num * nper
+    A = np.zeros((N, N))
+    for (i, j), rows in zip(pairs, corres):
+        if len(rows) == 0:
+            continue
+        idx1, v1, idx2, v2 = nonrigid_rows(clouds[i], clouds[j], rows, weight)
+        for s in range(0, len(rows), chunk):
+            e = min(len(rows), s + chunk)
+            S1 = np.zeros((e - s, nper))
+            S2 = np.zeros((e - s, nper))
+            np.add.at(S1, (np.arange(e - s)[:, None], idx1[s:e]), v1[s:e])
+            np.add.at(S2, (np.arange(e - s)[:, None], idx2[s:e]), v2[s:e])
+            A[i * nper:(i + 1) * nper, i * nper:(i + 1) * nper] += S1.T @ S1
+            A[j * nper:(j + 1) * nper, j * nper:(j + 1) * nper] += S2.T @ S2
+            A[i * nper:(i + 1) * nper, j * nper:(j + 1) * nper] += S1.T @ S2
+    return np.triu(A)
+
+
+def base_aa(L: Lattice, num):
+    """COptApp::InitBaseAA (OptApp.cpp:765-811), upper triangle."""
+    N = num * L.nper
+    B = np.zeros((N, N))
+    for l in range(num):
+        off = l * L.nper
+        for i in range(L.r1):
+            for j in range(L.r1):
+                for k in range(L.r1):
+                    u = L.node(i, j, k) * 3 + off
+                    for v in lattice_neighbours(L, i, j, k):
+                        v = v * 3 + off
+                        for x in range(3):
+                            B[u + x, u + x] += 1
+                            B[v + x, v + x] += 1
+                            B[min(u, v) + x, max(u, v) + x] += -1
+        if l == 0:
+            for x in range(3):
+                B[x, x] += 1
+    return B
+
+
+def nonrigid_rhs(L: Lattice, num, ictr, ctr):
+    """The inner iteration's Ab (OptApp.cpp:221-259)."""
+    Ab = np.zeros(num * L.nper)
+    for l in range(num):
+        off = l * L.nper
+        for i in range(L.r1):
+            for j in range(L.r1):
+                for k in range(L.r1):
+                    u = L.node(i, j, k) * 3 + off
+                    nb = [v * 3 + off for v in lattice_neighbours(L, i, j, k)]
+                    d0 = np.array([ictr[u:u + 3] - ictr[v:v + 3] for v in nb])
+                    d1 = np.array([ctr[u:u + 3] - ctr[v:v + 3] for v in nb])
+                    R = get_rotation(d0, d1)
+                    for t, v in enumerate(nb):
+                        bx = R @ d0[t]
+                        Ab[u:u + 3] += bx
+                        Ab[v:v + 3] -= bx
+    return Ab
+
+
+def optimize_nonrigid(xyzn, pairs, corres, ipose, resolution=8, length=3.0, weight=1.0, iterations=5, inner_iterations=10, trace=None):
+    """OptimizeNonrigid (OptApp.cpp:120-278).  Returns the lattices [num*nper/3, 3]."""
+    from scipy.linalg import cho_factor, cho_solve
+    num = len(xyzn)
+    L = Lattice(resolution, length)
+    clouds = [Cloud(L, c) for c in xyzn]
+    lat = np.array([[i * L.unit_d, j * L.unit_d, k * L.unit_d] for k in range(L.r1) for j in range(L.r1) for i in range(L.r1)])
+    ctr = np.concatenate([lat @ np.asarray(ipose[l])[:3, :3].T + np.asarray(ipose[l])[:3, 3] for l in range(num)]).reshape(-1)
+    ictr = ctr.copy()
+    B = base_aa(L, num)
+    for itr in range(iterations):
+        for l in range(num):
+            clouds[l].update_normal(ctr[l * L.nper:(l + 1) * L.nper])
+        A = nonrigid_data_matrix(clouds, pairs, corres, L.nper, weight)
+        if trace is not None:
+            trace.append({"A": A, "normals": [c.n.copy() for c in clouds]})
+        F = cho_factor((A + B).T, lower=True)                 # the stored upper triangle, read as the lower one of the transpose
+        for m in range(inner_iterations):
+            ctr = cho_solve(F, nonrigid_rhs(L, num, ictr, ctr))
+    return ctr.reshape(-1, 3)

@@ -44,6 +44,8 @@ struct er_fragopt {
   std::vector<long long> pair_start;
   std::vector<Corr> corr;                         // sorted
   std::vector<double> JJ, base;
+  std::vector<double> AA;                         // nonrigid: dense N x N (upper), Cholesky factor after nr_factor
+  bool nr_factored = false;
   bool have_base = false;
   int emul_ctas = 7;                              // ranges of the persistent CTAs (any value must give the same sums)
   uint64_t launches = 0, flushes = 0;
@@ -301,6 +303,111 @@ int er_fragopt_rigid_assemble(er_fragopt* h, double* JJ, double* Jb, double* sco
     *score += s[90];
   }
   ++h->launches;
+  return ER_OK;
+}
+
+// nonrigid_assemble_kernel, CTA after CTA
+int er_fragopt_nonrigid_assemble(er_fragopt* h, double weight) {
+  const long long N = (long long)h->num * h->L.nper;
+  h->AA.assign((size_t)N * N, 0.0);
+  h->nr_factored = false;
+  h->flushes = 0;
+  const long long total = (long long)h->corr.size();
+  const long long batches = (total + kNrThreads - 1) / kNrThreads;
+  const int grid = (int)std::min<long long>(batches, h->emul_ctas);
+  std::vector<double> rows((size_t)kNrThreads * kNrStride);
+  std::vector<SlacKey> keys(kNrThreads);
+  std::vector<int> brk(kNrThreads);
+  for (int cta = 0; cta < grid; ++cta) {
+    const long long begin = total * (long long)cta / grid, end = total * (long long)(cta + 1) / grid;
+    double acc[kNrThreads][16];
+    int ty[kNrThreads], tx[kNrThreads];
+    for (int tid = 0; tid < kNrThreads; ++tid) {
+      fo_nr_tile_of(tid < kNrTiles ? tid : 0, &ty[tid], &tx[tid]);
+      for (int e = 0; e < 16; ++e) acc[tid][e] = 0.0;
+    }
+    SlacKey cur;
+    cur.pair = -1; cur.bi = -1; cur.bj = -1;
+    auto flush = [&]() {
+      for (int tid = 0; tid < kNrThreads; ++tid)
+        fo_nr_flush(h->L, N, h->pair_i[cur.pair], h->pair_j[cur.pair], cur, tid, ty[tid], tx[tid], acc[tid], h->AA.data(), HostAdd());
+      ++h->flushes;
+    };
+    for (long long base = begin; base < end; base += kNrThreads) {
+      const int cnt = (int)std::min<long long>(kNrThreads, end - base);
+      for (int tid = 0; tid < cnt; ++tid) {
+        const Corr& c = h->corr[base + tid];
+        const StaticPoint &si = h->S[c.gi], &sj = h->S[c.gj];
+        fo_nonrigid_row(si.r, &h->N[3 * c.gi], sj.r, weight, &rows[(size_t)tid * kNrStride]);
+        keys[tid].pair = c.pair; keys[tid].bi = si.base; keys[tid].bj = sj.base;
+      }
+      for (int tid = 0; tid < cnt; ++tid) brk[tid] = !(keys[tid] == (tid == 0 ? cur : keys[tid - 1]));
+      for (int c = 0; c < cnt; ++c) {
+        if (brk[c]) {
+          if (cur.pair >= 0) flush();
+          for (int tid = 0; tid < kNrThreads; ++tid) for (int e = 0; e < 16; ++e) acc[tid][e] = 0.0;
+          cur = keys[c];
+        }
+        for (int tid = 0; tid < kNrTiles; ++tid) fo_tile_mac<kNrStride>(ty[tid], tx[tid], &rows[(size_t)c * kNrStride], acc[tid]);
+      }
+    }
+    if (cur.pair >= 0) flush();
+  }
+  ++h->launches;
+  return ER_OK;
+}
+
+int er_fragopt_nonrigid_get_aa(er_fragopt* h, double* aa) {
+  if (h->AA.empty() || h->nr_factored) { set_err("er_fragopt_nonrigid_get_aa: assemble first (and before factoring)"); return ER_ERR_ARG; }
+  memcpy(aa, h->AA.data(), h->AA.size() * sizeof(double));
+  return ER_OK;
+}
+
+// in-place Cholesky of the upper triangle (A = U^T U), then solves against the stored factor
+static bool chol_factor(int n, std::vector<double>& A) {
+  for (int k = 0; k < n; ++k) {
+    double d = A[(size_t)k * n + k];
+    for (int s = 0; s < k; ++s) d -= A[(size_t)s * n + k] * A[(size_t)s * n + k];
+    if (!(d > 0)) return false;
+    d = sqrt(d);
+    A[(size_t)k * n + k] = d;
+#pragma omp parallel for schedule(static)
+    for (int c = k + 1; c < n; ++c) {
+      double v = A[(size_t)k * n + c];
+      for (int s = 0; s < k; ++s) v -= A[(size_t)s * n + k] * A[(size_t)s * n + c];
+      A[(size_t)k * n + c] = v / d;
+    }
+  }
+  return true;
+}
+
+int er_fragopt_nonrigid_factor(er_fragopt* h, size_t nnz, const int32_t* rows, const int32_t* cols, const double* vals) {
+  if (h->AA.empty() || h->nr_factored) { set_err("er_fragopt_nonrigid_factor: assemble first"); return ER_ERR_ARG; }
+  const long long N = (long long)h->num * h->L.nper;
+  for (size_t k = 0; k < nnz; ++k) {
+    if (rows[k] < 0 || rows[k] > cols[k] || cols[k] >= N) { set_err("er_fragopt_nonrigid_factor: triplets must lie in the upper triangle"); return ER_ERR_ARG; }
+    h->AA[(size_t)rows[k] * N + cols[k]] += vals[k];
+  }
+  if (!chol_factor((int)N, h->AA)) { set_err("er_fragopt_nonrigid_factor: not positive definite"); return ER_ERR_ARG; }
+  h->nr_factored = true;
+  return ER_OK;
+}
+
+int er_fragopt_nonrigid_solve(er_fragopt* h, const double* rhs, double* x) {
+  if (!h->nr_factored) { set_err("er_fragopt_nonrigid_solve: factor first"); return ER_ERR_ARG; }
+  const int n = h->num * h->L.nper;
+  const std::vector<double>& A = h->AA;
+  std::vector<double> y(n);
+  for (int k = 0; k < n; ++k) {
+    double v = rhs[k];
+    for (int s = 0; s < k; ++s) v -= A[(size_t)s * n + k] * y[s];
+    y[k] = v / A[(size_t)k * n + k];
+  }
+  for (int k = n - 1; k >= 0; --k) {
+    double v = y[k];
+    for (int c = k + 1; c < n; ++c) v -= A[(size_t)k * n + c] * x[c];
+    x[k] = v / A[(size_t)k * n + k];
+  }
   return ER_OK;
 }
 

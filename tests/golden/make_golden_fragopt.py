@@ -21,16 +21,16 @@ import pyoracle         # noqa: E402
 def main():
     pyoracle.build()
     out = {}
-    for name in helpers.FRAGOPT_CASES:
-        for mode in ("slac", "rigid"):
-            with tempfile.TemporaryDirectory() as d:
-                _, args = helpers.fragopt_case(name, d)
-                log = pyoracle.run_reference_fragopt(args + ["--" + mode], cwd=d, threads=1)
+    for name, mode in helpers.FRAGOPT_CASE_MODES:
+        with tempfile.TemporaryDirectory() as d:
+            _, args = helpers.fragopt_case(name, d)
+            log = pyoracle.run_reference_fragopt(args + ["--" + mode], cwd=d, threads=1)
+            if mode != "nonrigid":                             # OptimizeNonrigid writes no pose.log
                 out["%s_%s_pose" % (name, mode)] = helpers.read_log_poses(os.path.join(d, "pose.log"))
-                out["%s_%s_ctr" % (name, mode)] = np.loadtxt(os.path.join(d, "output.ctr"))
-                scores = [float(l.split(":")[1]) for l in log.splitlines() if "rror score is" in l]
-                out["%s_%s_scores" % (name, mode)] = np.array(scores)
-                print(name, mode, out["%s_%s_pose" % (name, mode)].shape, out["%s_%s_ctr" % (name, mode)].shape, scores)
+            out["%s_%s_ctr" % (name, mode)] = np.loadtxt(os.path.join(d, "output.ctr"))
+            scores = [float(l.split(" is ")[1].lstrip(": ")) for l in log.splitlines() if "score is" in l]
+            out["%s_%s_scores" % (name, mode)] = np.array(scores)
+            print(name, mode, out["%s_%s_ctr" % (name, mode)].shape, scores)
     np.savez_compressed(os.path.join(ROOT, "tests", "golden", "fragopt_golden.npz"), **out)
 
 

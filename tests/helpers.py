@@ -154,9 +154,14 @@ def run_scene(vol, sc, mul=None):
 # ----------------------------------------------------------------------------------------------- FragmentOptimizer cases
 FRAGOPT_CASES = {
     # name: (num, points per fragment, extra flags, pcd input, blacklist)
-    "three": dict(num=3, n_points=6000, pcd=False, blacklist=None, flags=["--iteration", "2"]),
-    "four_pcd_blacklist": dict(num=4, n_points=4000, pcd=True, blacklist=[3], flags=["--iteration", "2", "--weight", "0.5"]),
+    "three": dict(num=3, n_points=6000, pcd=False, blacklist=None, flags=["--iteration", "2"], modes=("slac", "rigid")),
+    "four_pcd_blacklist": dict(num=4, n_points=4000, pcd=True, blacklist=[3], flags=["--iteration", "2", "--weight", "0.5"],
+                               modes=("slac", "rigid")),
+    # the nonrigid system is dense here (num * 3 (res+1)^3 unknowns): resolution 4 keeps the CPU emulation's Cholesky small
+    "three_res4": dict(num=3, n_points=6000, pcd=False, blacklist=None,
+                       flags=["--iteration", "2", "--inner_iteration", "3", "--resolution", "4", "--weight", "2.0"], modes=("nonrigid",)),
 }
+FRAGOPT_CASE_MODES = [(n, m) for n, c in FRAGOPT_CASES.items() for m in c["modes"]]
 
 
 def fragopt_case(name: str, out_dir: str):

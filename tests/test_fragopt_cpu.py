@@ -69,8 +69,7 @@ def flag(c, name, default):
     return type(default)(c["flags"][c["flags"].index(name) + 1]) if name in c["flags"] else default
 
 
-@pytest.mark.parametrize("name", list(helpers.FRAGOPT_CASES))
-@pytest.mark.parametrize("mode", ["slac", "rigid"])
+@pytest.mark.parametrize("name,mode", helpers.FRAGOPT_CASE_MODES)
 def test_numpy_oracle_matches_reference_binary(golden, tmp_path, name, mode):
     import fragopt_oracle as fo
     d, _ = helpers.fragopt_case(name, str(tmp_path))
@@ -78,31 +77,42 @@ def test_numpy_oracle_matches_reference_binary(golden, tmp_path, name, mode):
     it = flag(c, "--iteration", 5)
     if mode == "slac":
         pose, ctr = fo.optimize_slac(xyzn, pairs, corres, ipose, iterations=it, weight=flag(c, "--weight", 1.0), num_before_blacklist=c["num"])
-    else:
+    elif mode == "rigid":
         pose, ctr = fo.optimize_rigid(xyzn, pairs, corres, ipose, iterations=it)
-    assert np.abs(pose - golden["%s_%s_pose" % (name, mode)]).max() <= POSE_TOL
+    else:
+        pose = None
+        ctr = fo.optimize_nonrigid(xyzn, pairs, corres, ipose, resolution=flag(c, "--resolution", 8), weight=flag(c, "--weight", 1.0),
+                                   iterations=it, inner_iterations=flag(c, "--inner_iteration", 10))
+    if pose is not None:
+        assert np.abs(pose - golden["%s_%s_pose" % (name, mode)]).max() <= POSE_TOL
     assert np.abs(ctr - golden["%s_%s_ctr" % (name, mode)]).max() <= CTR_TOL
 
 
-@pytest.mark.parametrize("name", list(helpers.FRAGOPT_CASES))
-@pytest.mark.parametrize("mode", ["slac", "rigid"])
-def test_emulated_executable_matches_reference_binary(oracle, emul, golden, tmp_path, name, mode):
-    d = str(tmp_path)
+def check_executable(exe, oracle, golden, d, name, mode):
+    """Shared with tests/test_fragopt_gpu.py: run `exe` on a case and compare its files with the reference binary's."""
     _, args = helpers.fragopt_case(name, d)
-    p = subprocess.run([emul["exe"]] + args + ["--" + mode, "--bench_json", os.path.join(d, "t.json")], cwd=d, stdout=subprocess.PIPE,
+    p = subprocess.run([exe] + args + ["--" + mode, "--bench_json", os.path.join(d, "t.json")], cwd=d, stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=900)
     assert p.returncode == 0, p.stdout
-    pose = helpers.read_log_poses(os.path.join(d, "pose.log"))
+    pose = helpers.read_log_poses(os.path.join(d, "pose.log")) if mode != "nonrigid" else None
     ctr = np.loadtxt(os.path.join(d, "output.ctr"))
-    assert np.abs(pose - golden["%s_%s_pose" % (name, mode)]).max() <= POSE_TOL
+    if pose is not None:
+        assert np.abs(pose - golden["%s_%s_pose" % (name, mode)]).max() <= POSE_TOL
     assert np.abs(ctr - golden["%s_%s_ctr" % (name, mode)]).max() <= CTR_TOL
-    scores = [float(l.split(":")[1]) for l in p.stdout.splitlines() if "rror score is" in l]
-    assert np.allclose(scores, golden["%s_%s_scores" % (name, mode)], atol=0.0101)          # printed with two decimals
+    scores = [float(l.split(" is ")[1].lstrip(": ")) for l in p.stdout.splitlines() if "score is" in l]
+    assert np.allclose(scores, golden["%s_%s_scores" % (name, mode)], atol=0.0101 if mode != "nonrigid" else 0.000101)   # printed digits
     if os.path.exists(oracle.REF_FRAGOPT):                                                   # and live, where the reference is built
-        os.rename(os.path.join(d, "pose.log"), os.path.join(d, "mine_pose.log"))
+        if pose is not None:
+            os.rename(os.path.join(d, "pose.log"), os.path.join(d, "mine_pose.log"))
         oracle.run_reference_fragopt(args + ["--" + mode], cwd=d)
-        assert np.abs(pose - helpers.read_log_poses(os.path.join(d, "pose.log"))).max() <= POSE_TOL
+        if pose is not None:
+            assert np.abs(pose - helpers.read_log_poses(os.path.join(d, "pose.log"))).max() <= POSE_TOL
         assert np.abs(ctr - np.loadtxt(os.path.join(d, "output.ctr"))).max() <= CTR_TOL
+
+
+@pytest.mark.parametrize("name,mode", helpers.FRAGOPT_CASE_MODES)
+def test_emulated_executable_matches_reference_binary(oracle, emul, golden, tmp_path, name, mode):
+    check_executable(emul["exe"], oracle, golden, str(tmp_path), name, mode)
 
 
 def test_emulated_kernels_against_the_oracle(emul, tmp_path):
@@ -184,6 +194,51 @@ def api_check(make, tmp_path, vary_emulated_ctas=False):
     assert abs(qscore - rscore) <= 1e-11 * rscore
 
 
+def nonrigid_api_check(make, tmp_path):
+    """Shared with the GPU tests: the nonrigid data matrix, factorisation and solves against the oracle."""
+    import fragopt_oracle as fo
+    d, _ = helpers.fragopt_case("three_res4", str(tmp_path))
+    xyzn, pairs, corres, ipose, _ = case_arrays("three_res4", d)
+    # a pair listed with idx0 > idx1 keeps only its diagonal blocks (its cross block lies in the lower triangle the solver never reads)
+    pairs = [pairs[0], (pairs[1][1], pairs[1][0]), pairs[2]]
+    corres = [corres[0], corres[1][:, ::-1].copy(), corres[2]]
+    num, res, weight = len(xyzn), 4, 2.0
+    L = fo.Lattice(res, 3.0)
+    N = num * L.nper
+    clouds = [fo.Cloud(L, c) for c in xyzn]
+    g = make(num, res)
+    for l in range(num):
+        g.set_cloud(l, xyzn[l])
+    g.set_pairs(pairs, corres)
+    lat = np.array([[i * L.unit_d, j * L.unit_d, k * L.unit_d] for k in range(L.r1) for j in range(L.r1) for i in range(L.r1)])
+    ctr = np.concatenate([lat @ ipose[l][:3, :3].T + ipose[l][:3, 3] for l in range(num)]).reshape(-1)
+    g.update_normals(ctr)
+    for l in range(num):
+        clouds[l].update_normal(ctr[l * L.nper:(l + 1) * L.nper])
+        assert np.array_equal(g.points(l)[:, 3:].view(np.uint32), clouds[l].n.view(np.uint32))
+    A = fo.nonrigid_data_matrix(clouds, pairs, corres, L.nper, weight)
+    g.nonrigid_assemble(weight)
+    gA = g.nonrigid_aa()
+    assert gA.shape == (N, N) and np.array_equal(gA, np.triu(gA))
+    assert np.abs(gA - A).max() <= 1e-11 * np.abs(A).max()
+    i1, j1 = pairs[1]
+    assert np.all(gA[j1 * L.nper:(j1 + 1) * L.nper, i1 * L.nper:(i1 + 1) * L.nper] == 0)          # the dropped cross block
+    B = fo.base_aa(L, num)
+    r, c = np.nonzero(B)
+    g.nonrigid_factor(r, c, B[r, c])
+    full = A + B
+    full = full + np.triu(full, 1).T
+    for k in range(2):
+        rhs = np.cos(0.37 * (k + 1) * np.arange(N))
+        x = g.nonrigid_solve(rhs)
+        assert np.abs(x - np.linalg.solve(full, rhs)).max() <= 1e-8 * max(1.0, np.abs(x).max())
+
+
+def test_emulated_nonrigid_kernels_against_the_oracle(emul, tmp_path):
+    from elasticreconstruction_b200 import capi
+    nonrigid_api_check(lambda num, res: capi.FragOpt(num, res, 3.0, library=emul["lib"]), tmp_path)
+
+
 def test_out_of_bound_point_stops_loading(emul):
     """PointCloud.cpp:37-40: the first point outside [0, length)^3 ends the cloud (it stays as a zero-filled record)."""
     from elasticreconstruction_b200 import capi
@@ -198,11 +253,11 @@ def test_out_of_bound_point_stops_loading(emul):
     assert g3.set_cloud(0, xyzn) == 4
 
 
-def test_executable_help_and_missing_mode(emul, tmp_path):
+def test_executable_help_and_missing_inputs(emul, tmp_path):
     p = subprocess.run([emul["exe"]], stdout=subprocess.PIPE, text=True)
     assert p.returncode == 0 and "--blasklist <blacklist_file>" in p.stdout and "--slac" in p.stdout
     p = subprocess.run([emul["exe"], "--num", "2"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, cwd=str(tmp_path))
-    assert p.returncode == 2 and "not implemented" in p.stdout
+    assert p.returncode == 1 and "trajectory is empty" in p.stdout          # the default mode is nonrigid; nothing to optimise without inputs
 
 
 def test_bench_loop_on_the_emulated_library_matches_reference_binary(emul, golden, tmp_path):

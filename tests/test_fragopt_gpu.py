@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import helpers
-from test_fragopt_cpu import CTR_TOL, POSE_TOL, api_check, case_arrays
+from test_fragopt_cpu import api_check, check_executable, nonrigid_api_check
 
 pytestmark = pytest.mark.gpu
 
@@ -23,26 +23,14 @@ def test_kernels_against_the_oracle(tmp_path):
     api_check(lambda num: capi.FragOpt(num, 8, 3.0, device=0), tmp_path)
 
 
-@pytest.mark.parametrize("name", list(helpers.FRAGOPT_CASES))
-@pytest.mark.parametrize("mode", ["slac", "rigid"])
+def test_nonrigid_kernels_against_the_oracle(tmp_path):
+    from elasticreconstruction_b200 import capi
+    nonrigid_api_check(lambda num, res: capi.FragOpt(num, res, 3.0, device=0), tmp_path)
+
+
+@pytest.mark.parametrize("name,mode", helpers.FRAGOPT_CASE_MODES)
 def test_executable_matches_reference_binary(oracle, tmp_path, name, mode):
-    golden = np.load(GOLDEN)
-    d = str(tmp_path)
-    _, args = helpers.fragopt_case(name, d)
-    p = subprocess.run([EXE] + args + ["--" + mode, "--bench_json", os.path.join(d, "t.json")], cwd=d, stdout=subprocess.PIPE,
-                       stderr=subprocess.STDOUT, text=True, timeout=600)
-    assert p.returncode == 0, p.stdout
-    pose = helpers.read_log_poses(os.path.join(d, "pose.log"))
-    ctr = np.loadtxt(os.path.join(d, "output.ctr"))
-    assert np.abs(pose - golden["%s_%s_pose" % (name, mode)]).max() <= POSE_TOL
-    assert np.abs(ctr - golden["%s_%s_ctr" % (name, mode)]).max() <= CTR_TOL
-    scores = [float(l.split(":")[1]) for l in p.stdout.splitlines() if "rror score is" in l]
-    assert np.allclose(scores, golden["%s_%s_scores" % (name, mode)], atol=0.0101)
-    if os.path.exists(oracle.REF_FRAGOPT):
-        os.rename(os.path.join(d, "pose.log"), os.path.join(d, "mine_pose.log"))
-        oracle.run_reference_fragopt(args + ["--" + mode], cwd=d)
-        assert np.abs(pose - helpers.read_log_poses(os.path.join(d, "pose.log"))).max() <= POSE_TOL
-        assert np.abs(ctr - np.loadtxt(os.path.join(d, "output.ctr"))).max() <= CTR_TOL
+    check_executable(EXE, oracle, np.load(GOLDEN), str(tmp_path), name, mode)
 
 
 def test_sample_file_and_sorted_order_independence(tmp_path):
