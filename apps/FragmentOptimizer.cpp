@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <set>
 #include <string>
 #include <vector>
@@ -29,6 +30,7 @@ struct Options {
   std::string blacklist_file, ipose_file, bench_json;
   int num = 0, resolution = 8, interval = 50, max_iteration = 5, max_inner_iteration = 10, sample_num = -1, blacklist_pair_num = 10000;
   int device = 0;
+  std::vector<int> devices;          // --devices a,b,...: the pair list is dealt over these GPUs (--slac, --rigid)
   double weight = 1.0, length = 3.0;
 };
 
@@ -58,6 +60,7 @@ int print_help() {
   printf("    --slac                          : simultaneous localization and calibration, published in CVPR 2014\n");
   printf("Added by this implementation:\n");
   printf("    --device <id>                   : CUDA device, default 0\n");
+  printf("    --devices <a,b,...>             : several GPUs: every GPU holds all fragments and a share of the pairs (--slac, --rigid)\n");
   printf("    --bench_json <file>             : write phase timings as JSON\n");
   return 0;
 }
@@ -168,7 +171,17 @@ struct App {
   int num = 0, nper = 0, r1 = 0;
   double unit = 0;
   std::vector<double> ipose, pose;              // num x 16
-  er_fragopt* h = nullptr;
+  er_fragopt* h = nullptr;                       // hs[0]: the handle that solves (and the only one in --nonrigid mode)
+  std::vector<er_fragopt*> hs;                   // one per device
+
+  // runs f on every handle, one host thread per device; false (after printing the library's message) if any call fails
+  bool on_all(const std::function<int(er_fragopt*, int)>& f) {
+    int bad = 0;
+#pragma omp parallel for num_threads((int)hs.size()) schedule(static, 1) reduction(+ : bad)
+    for (int d = 0; d < (int)hs.size(); ++d)
+      if (f(hs[d], d) != ER_OK) { fprintf(stderr, "%s\n", er_last_error()); ++bad; }
+    return bad == 0;
+  }
   std::vector<size_t> cloud_size;
   int npairs = 0;
   double t_load = 0, t_assemble = 0, t_solve = 0, t_update = 0, t_reg = 0;
@@ -257,7 +270,7 @@ struct App {
       if (state[i] == 3) fprintf(stderr, "File not found ... Check dir and num parameters.\n");
       size_t kept = 0;
       const size_t n = rows[i].size() / 6;
-      if (er_fragopt_set_cloud(h, i, rows[i].data(), n, &kept) != ER_OK) { fprintf(stderr, "%s\n", er_last_error()); return false; }
+      if (!on_all([&](er_fragopt* g, int) { return er_fragopt_set_cloud(g, i, rows[i].data(), n, &kept); })) return false;
       if (kept != n) fprintf(stderr, "Error!! Point out of bound!!\n");
       else if (state[i] == 1) printf("Read cloud %d ... get %zu points.\n", ii, kept);
       cloud_size[i] = kept;
@@ -328,11 +341,35 @@ struct App {
     for (int p = 0; p < npairs; ++p)
       if (!rows[p].empty()) memcpy(&all[2 * start[p]], rows[p].data(), rows[p].size() * sizeof(int32_t));
     rows_total = start[npairs];
-    if (er_fragopt_set_pairs(h, npairs, idx0.data(), idx1.data(), start.data(), all.data()) != ER_OK) {
-      fprintf(stderr, "%s\n", er_last_error());
-      return false;
+    if (hs.size() == 1) {
+      if (er_fragopt_set_pairs(h, npairs, idx0.data(), idx1.data(), start.data(), all.data()) != ER_OK) {
+        fprintf(stderr, "%s\n", er_last_error());
+        return false;
+      }
+      return true;
     }
-    return true;
+    // several devices: longest pair first onto the least loaded device; a device keeps its pairs in list order
+    std::vector<int> order(npairs), owner(npairs, 0);
+    for (int p = 0; p < npairs; ++p) order[p] = p;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return rows[a].size() > rows[b].size(); });
+    std::vector<size_t> load(hs.size(), 0);
+    for (int p : order) {
+      const int d = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+      owner[p] = d;
+      load[d] += rows[p].size() / 2 + 1;
+    }
+    return on_all([&](er_fragopt* g, int d) {
+      std::vector<int> i0, i1;
+      std::vector<size_t> st(1, 0);
+      std::vector<int32_t> mine;
+      for (int p = 0; p < npairs; ++p)
+        if (owner[p] == d) {
+          i0.push_back(idx0[p]); i1.push_back(idx1[p]);
+          mine.insert(mine.end(), rows[p].begin(), rows[p].end());
+          st.push_back(st.back() + rows[p].size() / 2);
+        }
+      return er_fragopt_set_pairs(g, (int)i0.size(), i0.data(), i1.data(), st.data(), mine.data());
+    });
   }
   size_t rows_total = 0;
 
@@ -452,8 +489,17 @@ struct App {
     unit = o.length / o.resolution;
     r1 = o.resolution + 1;
     nper = r1 * r1 * r1 * 3;
-    h = er_fragopt_create(o.device, num, o.resolution, o.length);
-    if (!h) { fprintf(stderr, "%s\n", er_last_error()); return false; }
+    std::vector<int> devs = o.devices.empty() ? std::vector<int>(1, o.device) : o.devices;
+    if (matrix_mode == 2 && devs.size() > 1) {
+      fprintf(stderr, "--nonrigid keeps its dense system on one GPU: using device %d only.\n", devs[0]);
+      devs.resize(1);
+    }
+    for (int dev : devs) {
+      er_fragopt* g = er_fragopt_create(dev, num, o.resolution, o.length);
+      if (!g) { fprintf(stderr, "%s\n", er_last_error()); return false; }
+      hs.push_back(g);
+    }
+    h = hs[0];
     const double t0 = now_ms();
     const bool ok = init_ipose() && init_pointclouds() && init_correspondences();
     t_load = now_ms() - t0;
@@ -507,7 +553,7 @@ struct App {
     pose = ipose;
     pose.resize((size_t)num * 16);
     refresh_rot();
-    if (er_fragopt_update_pose(h, pose.data()) != ER_OK) { fprintf(stderr, "%s\n", er_last_error()); return 1; }
+    if (!on_all([&](er_fragopt* g, int) { return er_fragopt_update_pose(g, pose.data()); })) return 1;
 
     const double t_neat = now_ms();
     // baseJJ * default_weight plus the six ones on the first fragment's pose (OptApp.cpp:449-464): every lattice edge
@@ -537,7 +583,18 @@ struct App {
       double t0 = now_ms();
       double score = 0.0;
       printf("Processing %d ... ", npairs);
-      if (er_fragopt_slac_assemble(h, rot_t.data(), Jb.data(), &score) != ER_OK) { fprintf(stderr, "%s\n", er_last_error()); return 1; }
+      {
+        std::vector<std::vector<double>> jbs(hs.size(), std::vector<double>(M));
+        std::vector<double> scores(hs.size(), 0.0);
+        if (!on_all([&](er_fragopt* g, int d) { return er_fragopt_slac_assemble(g, rot_t.data(), jbs[d].data(), &scores[d]); })) return 1;
+        Jb = jbs[0];
+        score = scores[0];
+        for (size_t d = 1; d < hs.size(); ++d) {              // device order: the sums do not depend on thread timing
+          if (er_fragopt_slac_accumulate(h, hs[d]) != ER_OK) { fprintf(stderr, "%s\n", er_last_error()); return 1; }
+          for (int e = 0; e < M; ++e) Jb[e] += jbs[d][e];
+          score += scores[d];
+        }
+      }
       {
         float ms = 0;
         uint64_t r = 0, fl = 0;
@@ -582,7 +639,7 @@ struct App {
       apply_increments(result, nullptr);
       refresh_rot();
       expand_ctr(this_ctr, expand);
-      if (er_fragopt_update_points_pn(h, expand.data()) != ER_OK) { fprintf(stderr, "%s\n", er_last_error()); return 1; }
+      if (!on_all([&](er_fragopt* g, int) { return er_fragopt_update_points_pn(g, expand.data()); })) return 1;
       t_update += now_ms() - t0;
       ++iterations_run;
     }
@@ -602,13 +659,23 @@ struct App {
     const int n6 = 6 * num;
     pose = ipose;
     pose.resize((size_t)num * 16);
-    if (er_fragopt_update_pose(h, pose.data()) != ER_OK) { fprintf(stderr, "%s\n", er_last_error()); return 1; }
+    if (!on_all([&](er_fragopt* g, int) { return er_fragopt_update_pose(g, pose.data()); })) return 1;
     std::vector<double> JJ((size_t)n6 * n6), Jb(n6), result(n6), inc;
     for (int itr = 0; itr < o.max_iteration; ++itr) {
       double t0 = now_ms();
       double score = 0.0;
       printf("Processing %d ... ", npairs);
-      if (er_fragopt_rigid_assemble(h, JJ.data(), Jb.data(), &score) != ER_OK) { fprintf(stderr, "%s\n", er_last_error()); return 1; }
+      {
+        std::vector<std::vector<double>> jjs(hs.size(), std::vector<double>((size_t)n6 * n6)), jbs(hs.size(), std::vector<double>(n6));
+        std::vector<double> scores(hs.size(), 0.0);
+        if (!on_all([&](er_fragopt* g, int d) { return er_fragopt_rigid_assemble(g, jjs[d].data(), jbs[d].data(), &scores[d]); })) return 1;
+        JJ = jjs[0]; Jb = jbs[0]; score = scores[0];
+        for (size_t d = 1; d < hs.size(); ++d) {
+          for (size_t e = 0; e < JJ.size(); ++e) JJ[e] += jjs[d][e];
+          for (int e = 0; e < n6; ++e) Jb[e] += jbs[d][e];
+          score += scores[d];
+        }
+      }
       for (int k = 0; k < 6 && k < n6; ++k) JJ[(size_t)k * n6 + k] += (double)npairs;       // mat_adder.Add(k, k, 1) once per pair
       t_assemble += now_ms() - t0;
       printf("Done.\n");
@@ -619,7 +686,7 @@ struct App {
       t_solve += now_ms() - t0;
       t0 = now_ms();
       apply_increments(result, &inc);
-      if (er_fragopt_update_pose(h, inc.data()) != ER_OK) { fprintf(stderr, "%s\n", er_last_error()); return 1; }
+      if (!on_all([&](er_fragopt* g, int) { return er_fragopt_update_pose(g, inc.data()); })) return 1;
       t_update += now_ms() - t0;
       ++iterations_run;
     }
@@ -758,6 +825,18 @@ int main(int argc, char** argv) {
   parse_argument(argc, argv, "--write_xyzn_sample", o.sample_num);
   parse_argument(argc, argv, "--blacklistpair", o.blacklist_pair_num);
   parse_argument(argc, argv, "--device", o.device);
+  {
+    std::string list;
+    if (parse_argument(argc, argv, "--devices", list) > 0) {
+      for (size_t p = 0; p < list.size();) {
+        const size_t q = list.find(',', p);
+        const std::string tok = list.substr(p, q == std::string::npos ? std::string::npos : q - p);
+        if (!tok.empty()) o.devices.push_back(atoi(tok.c_str()));
+        if (q == std::string::npos) break;
+        p = q + 1;
+      }
+    }
+  }
   parse_argument(argc, argv, "--bench_json", o.bench_json);
   if (parse_argument(argc, argv, "--blacklist", o.blacklist_file) > 0) {           // COptApp::Blacklist
     FILE* f = fopen(o.blacklist_file.c_str(), "r");
@@ -787,13 +866,13 @@ int main(int argc, char** argv) {
     if (f) {
       fprintf(f, "{\"mode\": \"%s\", \"rc\": %d, \"fragments\": %d, \"pairs\": %d, \"correspondences\": %zu, \"iterations\": %d, "
                  "\"total_ms\": %.3f, \"load_ms\": %.3f, \"assemble_ms\": %.3f, \"assemble_kernel_ms\": %.3f, \"regulariser_ms\": %.3f, "
-                 "\"solve_ms\": %.3f, \"update_ms\": %.3f, \"rows_assembled\": %llu, \"flushes\": %llu, \"launches\": %llu}\n",
+                 "\"solve_ms\": %.3f, \"update_ms\": %.3f, \"rows_assembled\": %llu, \"flushes\": %llu, \"launches\": %llu, \"devices\": %zu}\n",
               mode, rc, app.num, app.npairs, app.rows_total, app.iterations_run, total, app.t_load, app.t_assemble, app.kernel_ms, app.t_reg,
               app.t_solve, app.t_update, (unsigned long long)app.rows, (unsigned long long)app.flushes,
-              (unsigned long long)(app.h ? er_fragopt_launch_count(app.h) : 0));
+              (unsigned long long)(app.h ? er_fragopt_launch_count(app.h) : 0), app.hs.size());
       fclose(f);
     }
   }
-  if (app.h) er_fragopt_destroy(app.h);
+  for (er_fragopt* g : app.hs) er_fragopt_destroy(g);
   return rc;
 }

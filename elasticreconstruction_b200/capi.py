@@ -96,6 +96,7 @@ SIGNATURES = {
     "er_fragopt_slac_assemble": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp]),
     "er_fragopt_slac_solve": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp]),
     "er_fragopt_slac_get_jj": (C.c_int, [C.c_void_p, c_dp]),
+    "er_fragopt_slac_accumulate": (C.c_int, [C.c_void_p, C.c_void_p]),
     "er_fragopt_rigid_assemble": (C.c_int, [C.c_void_p, c_dp, c_dp, c_dp]),
     "er_fragopt_nonrigid_assemble": (C.c_int, [C.c_void_p, C.c_double]),
     "er_fragopt_nonrigid_factor": (C.c_int, [C.c_void_p, C.c_size_t, c_i32p, c_i32p, c_dp]),
@@ -648,6 +649,10 @@ class FragOpt:
         score = C.c_double()
         self._check(self._L.er_fragopt_slac_assemble(self._h, _dp(r), _dp(Jb), C.byref(score)))
         return Jb, score.value
+
+    def slac_accumulate(self, other: "FragOpt"):
+        """self's assembled matrix += other's (several devices, er_fragopt_slac_accumulate)."""
+        self._check(self._L.er_fragopt_slac_accumulate(self._h, other._h))
 
     def slac_jj(self) -> np.ndarray:
         jj = np.empty((self.M, self.M), dtype=np.float64)

@@ -39,10 +39,10 @@ namespace {
 constexpr int kThreads = 128;
 // rows staged per batch (<= kThreads; 64 doubles of shared memory each) and resident CTAs per SM the kernel is compiled for
 #ifndef ER_FO_BATCH
-#define ER_FO_BATCH 128
+#define ER_FO_BATCH 96
 #endif
 #ifndef ER_FO_MINB
-#define ER_FO_MINB 3
+#define ER_FO_MINB 4
 #endif
 constexpr int kBatch = ER_FO_BATCH;
 static_assert(kBatch <= kThreads && kBatch % 32 == 0, "ER_FO_BATCH");
@@ -98,7 +98,7 @@ slac_assemble_kernel(FoView v, const double* __restrict__ rot_t, double* JJ, dou
       const float4 nn = v.nrm[c.x];
       const float ni[3] = {nn.x, nn.y, nn.z};
       const int i = __ldg(&v.pair_i[c.z]), j = __ldg(&v.pair_j[c.z]);
-      fo_slac_row(pi, ni, ri, pj, rj, rot_t + 9 * i, rot_t + 9 * j, &rows[tid * kRowStride]);
+      fo_slac_row(pi, ni, ri, pj, rj, rot_t + 9 * i, rot_t + 9 * j, &rows[tid * kRowStride], tid & 7);
       SlacKey k;
       k.pair = c.z; k.bi = bi; k.bj = bj;
       keys[tid] = k;
@@ -116,7 +116,7 @@ slac_assemble_kernel(FoView v, const double* __restrict__ rot_t, double* JJ, dou
         for (int e = 0; e < 16; ++e) acc[e] = 0.0;
         cur = keys[c];
       }
-      fo_slac_mac(tid, ty, tx, &rows[c * kRowStride], acc);
+      fo_slac_mac(tid, ty, tx, &rows[c * kRowStride], c & 7, acc);
     }
     __syncthreads();
   }
@@ -153,7 +153,7 @@ nonrigid_assemble_kernel(FoView v, double weight, long long N, double* A, unsign
       const float ri[3] = {__int_as_float(a.y), __int_as_float(a.z), __int_as_float(a.w)};
       const float rj[3] = {__int_as_float(b.y), __int_as_float(b.z), __int_as_float(b.w)};
       const float ni[3] = {nn.x, nn.y, nn.z};
-      fo_nonrigid_row(ri, ni, rj, weight, &rows[tid * kNrStride]);
+      fo_nonrigid_row(ri, ni, rj, weight, &rows[tid * kNrStride], tid & 7);
       SlacKey k;
       k.pair = c.z; k.bi = a.x; k.bj = b.x;
       keys[tid] = k;
@@ -171,7 +171,7 @@ nonrigid_assemble_kernel(FoView v, double weight, long long N, double* A, unsign
         for (int e = 0; e < 16; ++e) acc[e] = 0.0;
         cur = keys[c];
       }
-      if (tid < kNrTiles) fo_tile_mac<kNrStride>(ty, tx, &rows[c * kNrStride], acc);
+      if (tid < kNrTiles) fo_tile_mac<kNrStride>(ty, tx, &rows[c * kNrStride], c & 7, acc);
     }
     __syncthreads();
   }
@@ -300,6 +300,11 @@ __global__ void corr_gather_kernel(const int4* __restrict__ in, const unsigned i
   if (k < n) out[k] = in[order[k]];
 }
 
+__global__ void add_matrix_kernel(double* __restrict__ dst, const double* __restrict__ src, size_t n) {
+  const size_t k = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (k < n) dst[k] += src[k];
+}
+
 // A = base + data on the stored triangle (row-major upper = column-major lower for cuSOLVER)
 __global__ void add_upper_kernel(const double* __restrict__ base, const double* __restrict__ data, double* A, int M) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
@@ -369,6 +374,7 @@ struct er_fragopt {
   float* d_poses = nullptr;
   double* d_rigid = nullptr;
   double* d_AA = nullptr;            // nonrigid: dense N x N
+  double* d_peer = nullptr;          // er_fragopt_slac_accumulate: the other device's matrix
   double* d_nr_rhs = nullptr;
   long long nr_N = 0;
   bool nr_factored = false;
@@ -466,7 +472,7 @@ void er_fragopt_destroy(er_fragopt* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* ptrs[] = {h->d_statA, h->d_statB, h->d_pos, h->d_nrm, h->d_pair_i, h->d_pair_j, h->d_pair_start, h->d_corr, h->d_rot,
                   h->d_JJ, h->d_Jb, h->d_score, h->d_base, h->d_A, h->d_rhs, h->d_ctr, h->d_poses, h->d_rigid, h->d_flushes,
-                  h->d_work, h->d_info, h->d_AA, h->d_nr_rhs};
+                  h->d_work, h->d_info, h->d_AA, h->d_nr_rhs, h->d_peer};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (h->solver) solver_api().destroy(h->solver);
   for (int e = 0; e < 8; ++e) if (h->ev[e]) cudaEventDestroy(h->ev[e]);
@@ -682,6 +688,20 @@ int er_fragopt_slac_assemble(er_fragopt* h, const double* rot_t, double* Jb, dou
   ER_CUDA(cudaMemcpyAsync(Jb, h->d_Jb, sizeof(double) * h->M, cudaMemcpyDeviceToHost, h->stream));
   ER_CUDA(cudaMemcpyAsync(score, h->d_score, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   ER_CUDA(cudaStreamSynchronize(h->stream));
+  ER_CUDA(cudaGetLastError());
+  return ER_OK;
+}
+
+int er_fragopt_slac_accumulate(er_fragopt* dst, er_fragopt* src) {
+  ER_ARG(dst && src && dst != src && dst->d_JJ && src->d_JJ && dst->M == src->M, "er_fragopt_slac_accumulate: both handles must have assembled the same system");
+  const size_t n = (size_t)dst->M * dst->M;
+  ER_CUDA(cudaSetDevice(dst->device));
+  if (!dst->d_peer) ER_CUDA(cudaMalloc(&dst->d_peer, n * sizeof(double)));
+  // src's er_fragopt_slac_assemble returned synchronised; cudaMemcpyPeer stages through the host where peer access is unavailable
+  ER_CUDA(cudaMemcpyPeerAsync(dst->d_peer, dst->device, src->d_JJ, src->device, n * sizeof(double), dst->stream));
+  add_matrix_kernel<<<(unsigned)((n + 255) / 256), 256, 0, dst->stream>>>(dst->d_JJ, dst->d_peer, n);
+  ++dst->launches;
+  ER_CUDA(cudaStreamSynchronize(dst->stream));
   ER_CUDA(cudaGetLastError());
   return ER_OK;
 }

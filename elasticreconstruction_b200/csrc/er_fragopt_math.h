@@ -164,9 +164,26 @@ ER_FO_FN int fo_pos(int e) {
   return e;
 #endif
 }
+// Thread t of the staging phase writes row t, STRIDE doubles after row t - 1: with 64 doubles per row every lane of a store
+// hits the same bank (measured: the staging stores were 26 % of all shared-memory wavefronts, profiles/r2_slac_assemble_kernel_v2.txt).
+// The 16-byte words of row t are therefore permuted by XOR with (t & 7): eight consecutive rows spread over all 32 banks
+// (a 4-way conflict instead of a 32-way one); the accumulation loop reads row c with the same, CTA-uniform, key c & 7.
+#ifndef ER_FO_SWIZZLE
+#define ER_FO_SWIZZLE 1
+#endif
+template <int STRIDE>
+ER_FO_FN int fo_spos(int e, int sw) {
+#if ER_FO_SWIZZLE && ER_FO_PLANES
+  const int p = fo_pos<STRIDE>(e);
+  return (((p >> 1) ^ sw) << 1) | (p & 1);
+#else
+  (void)sw;
+  return fo_pos<STRIDE>(e);
+#endif
+}
 
 ER_FO_FN void fo_slac_row(const float pi[3], const float ni[3], const float ri[3], const float pj[3], const float rj[3],
-                          const double* rot_ti, const double* rot_tj, double* row) {
+                          const double* rot_ti, const double* rot_tj, double* row, int sw) {
   const double ppi[3] = {pi[0], pi[1], pi[2]}, ppj[3] = {pj[0], pj[1], pj[2]}, npi[3] = {ni[0], ni[1], ni[2]};
   const double d0 = ppi[0] - ppj[0], d1 = ppi[1] - ppj[1], d2 = ppi[2] - ppj[2];
   const double b = (d0 * npi[0] + d1 * npi[1]) + d2 * npi[2];
@@ -174,10 +191,10 @@ ER_FO_FN void fo_slac_row(const float pi[3], const float ni[3], const float ri[3
   const double t1 = ppj[2] * npi[0] - ppj[0] * npi[2];
   const double t2 = ppj[0] * npi[1] - ppj[1] * npi[0];
   constexpr int S = kRowStride;
-  row[fo_pos<S>(0)] = t0; row[fo_pos<S>(1)] = t1; row[fo_pos<S>(2)] = t2;
-  row[fo_pos<S>(3)] = npi[0]; row[fo_pos<S>(4)] = npi[1]; row[fo_pos<S>(5)] = npi[2];
-  row[fo_pos<S>(6)] = -t0; row[fo_pos<S>(7)] = -t1; row[fo_pos<S>(8)] = -t2;
-  row[fo_pos<S>(9)] = -npi[0]; row[fo_pos<S>(10)] = -npi[1]; row[fo_pos<S>(11)] = -npi[2];
+  row[fo_spos<S>(0, sw)] = t0; row[fo_spos<S>(1, sw)] = t1; row[fo_spos<S>(2, sw)] = t2;
+  row[fo_spos<S>(3, sw)] = npi[0]; row[fo_spos<S>(4, sw)] = npi[1]; row[fo_spos<S>(5, sw)] = npi[2];
+  row[fo_spos<S>(6, sw)] = -t0; row[fo_spos<S>(7, sw)] = -t1; row[fo_spos<S>(8, sw)] = -t2;
+  row[fo_spos<S>(9, sw)] = -npi[0]; row[fo_spos<S>(10, sw)] = -npi[1]; row[fo_spos<S>(11, sw)] = -npi[2];
   double dTi[3], dTj[3];
   for (int r = 0; r < 3; ++r) {
     dTi[r] = (rot_ti[3 * r] * npi[0] + rot_ti[3 * r + 1] * npi[1]) + rot_ti[3 * r + 2] * npi[2];
@@ -188,11 +205,11 @@ ER_FO_FN void fo_slac_row(const float pi[3], const float ni[3], const float ri[3
   fo_vals(rj, c);
   for (int ll = 0; ll < 8; ++ll)
     for (int xyz = 0; xyz < 3; ++xyz) {
-      row[fo_pos<S>(12 + ll * 3 + xyz)] = a[ll] * dTi[xyz];
-      row[fo_pos<S>(36 + ll * 3 + xyz)] = c[ll] * dTj[xyz];
+      row[fo_spos<S>(12 + ll * 3 + xyz, sw)] = a[ll] * dTi[xyz];
+      row[fo_spos<S>(36 + ll * 3 + xyz, sw)] = c[ll] * dTj[xyz];
     }
-  row[fo_pos<S>(60)] = b;
-  row[fo_pos<S>(61)] = 0.0; row[fo_pos<S>(62)] = 0.0; row[fo_pos<S>(63)] = 0.0;
+  row[fo_spos<S>(60, sw)] = b;
+  row[fo_spos<S>(61, sw)] = 0.0; row[fo_spos<S>(62, sw)] = 0.0; row[fo_spos<S>(63, sw)] = 0.0;
 }
 
 // The segment key: all correspondences with the same key share the 60 global column indices of their rows.
@@ -224,12 +241,17 @@ struct alignas(16) D2 { double x, y; };
 
 // acc[16] += a (x) b for the 4x4 tile (ty, tx) of row^T row
 template <int STRIDE>
-ER_FO_FN void fo_tile_mac(int ty, int tx, const double* row, double* acc) {
+ER_FO_FN void fo_tile_mac(int ty, int tx, const double* row, int sw, double* acc) {
   // four 128-bit shared-memory loads (rows are 16-byte aligned)
-#if ER_FO_PLANES
+#if ER_FO_PLANES && ER_FO_SWIZZLE
+  const D2 p0 = *reinterpret_cast<const D2*>(row + 2 * (ty ^ sw)), p1 = *reinterpret_cast<const D2*>(row + 2 * ((STRIDE / 4 + ty) ^ sw));
+  const D2 q0 = *reinterpret_cast<const D2*>(row + 2 * (tx ^ sw)), q1 = *reinterpret_cast<const D2*>(row + 2 * ((STRIDE / 4 + tx) ^ sw));
+#elif ER_FO_PLANES
+  (void)sw;
   const D2 p0 = *reinterpret_cast<const D2*>(row + 2 * ty), p1 = *reinterpret_cast<const D2*>(row + STRIDE / 2 + 2 * ty);
   const D2 q0 = *reinterpret_cast<const D2*>(row + 2 * tx), q1 = *reinterpret_cast<const D2*>(row + STRIDE / 2 + 2 * tx);
 #else
+  (void)sw;
   const D2 p0 = *reinterpret_cast<const D2*>(row + 4 * ty), p1 = *reinterpret_cast<const D2*>(row + 4 * ty + 2);
   const D2 q0 = *reinterpret_cast<const D2*>(row + 4 * tx), q1 = *reinterpret_cast<const D2*>(row + 4 * tx + 2);
 #endif
@@ -244,13 +266,13 @@ ER_FO_FN void fo_tile_mac(int ty, int tx, const double* row, double* acc) {
 }
 
 // one staged row: the tile threads add their tile, the eight vector threads acc[0..7] += b * row[8u..]
-ER_FO_FN void fo_slac_mac(int tid, int ty, int tx, const double* row, double* acc) {
+ER_FO_FN void fo_slac_mac(int tid, int ty, int tx, const double* row, int sw, double* acc) {
   if (tid < 120) {
-    fo_tile_mac<kRowStride>(ty, tx, row, acc);
+    fo_tile_mac<kRowStride>(ty, tx, row, sw, acc);
   } else {
-    const double b = row[fo_pos<kRowStride>(60)];
+    const double b = row[fo_spos<kRowStride>(60, sw)];
     const int u = tid - 120;
-    for (int e = 0; e < 8; ++e) acc[e] = fma(b, row[fo_pos<kRowStride>(8 * u + e)], acc[e]);
+    for (int e = 0; e < 8; ++e) acc[e] = fma(b, row[fo_spos<kRowStride>(8 * u + e, sw)], acc[e]);
   }
 }
 
@@ -317,14 +339,14 @@ constexpr int kNrStride = 48;
 constexpr int kNrThreads = 96;     // 78 of them own a 4x4 tile of the 12 x 12-tile upper triangle
 constexpr int kNrTiles = 78;
 
-ER_FO_FN void fo_nonrigid_row(const float ri[3], const float ni[3], const float rj[3], double weight, double* row) {
+ER_FO_FN void fo_nonrigid_row(const float ri[3], const float ni[3], const float rj[3], double weight, double* row, int sw) {
   float a[8], c[8];
   fo_vals(ri, a);
   fo_vals(rj, c);
   for (int t = 0; t < 3; ++t)
     for (int ll = 0; ll < 8; ++ll) {
-      row[fo_pos<kNrStride>(t * 8 + ll)] = a[ll] * weight * ni[t];
-      row[fo_pos<kNrStride>(24 + t * 8 + ll)] = -c[ll] * weight * ni[t];
+      row[fo_spos<kNrStride>(t * 8 + ll, sw)] = a[ll] * weight * ni[t];
+      row[fo_spos<kNrStride>(24 + t * 8 + ll, sw)] = -c[ll] * weight * ni[t];
     }
 }
 

@@ -278,6 +278,11 @@ int er_fragopt_slac_assemble(er_fragopt* h, const double* rot_t, double* Jb, dou
  * matrix_size_^2 doubles of which the upper triangle is read (baseJJ * default_weight plus the six ones of
  * OptApp.cpp:456-464); NULL = the matrix given last time. */
 int er_fragopt_slac_solve(er_fragopt* h, const double* base, const double* rhs, double* x);
+/* Several GPUs: every device holds a handle with ALL clouds and a share of the pairs (the pair loop of OptimizeSLAC shards like
+ * the ICP one); after each handle's er_fragopt_slac_assemble, dst's matrix += src's -- a peer copy of the matrix_size_^2
+ * doubles (49 MB for 50 fragments) into a buffer on dst's device and one add kernel there.  Jb and the score are host
+ * values the caller adds.  This is the one exchange step of the path. */
+int er_fragopt_slac_accumulate(er_fragopt* dst, er_fragopt* src);
 /* The assembled data term, upper triangle of a row-major matrix_size_^2 matrix (tests, diagnostics). */
 int er_fragopt_slac_get_jj(er_fragopt* h, double* jj);
 

@@ -205,7 +205,7 @@ int er_fragopt_slac_assemble(er_fragopt* h, const double* rot_t, double* Jb, dou
         const Corr& c = h->corr[base + tid];
         const StaticPoint &si = h->S[c.gi], &sj = h->S[c.gj];
         fo_slac_row(&h->P[3 * c.gi], &h->N[3 * c.gi], si.r, &h->P[3 * c.gj], sj.r, rot_t + 9 * h->pair_i[c.pair], rot_t + 9 * h->pair_j[c.pair],
-                    &rows[(size_t)tid * kRowStride]);
+                    &rows[(size_t)tid * kRowStride], tid & 7);
         keys[tid].pair = c.pair; keys[tid].bi = si.base; keys[tid].bj = sj.base;
       }
       for (int tid = 0; tid < cnt; ++tid) brk[tid] = !(keys[tid] == (tid == 0 ? cur : keys[tid - 1]));
@@ -215,12 +215,18 @@ int er_fragopt_slac_assemble(er_fragopt* h, const double* rot_t, double* Jb, dou
           for (int tid = 0; tid < kThreads; ++tid) for (int e = 0; e < 16; ++e) acc[tid][e] = 0.0;
           cur = keys[c];
         }
-        for (int tid = 0; tid < kThreads; ++tid) fo_slac_mac(tid, ty[tid], tx[tid], &rows[(size_t)c * kRowStride], acc[tid]);
+        for (int tid = 0; tid < kThreads; ++tid) fo_slac_mac(tid, ty[tid], tx[tid], &rows[(size_t)c * kRowStride], c & 7, acc[tid]);
       }
     }
     if (cur.pair >= 0) flush();
   }
   ++h->launches;
+  return ER_OK;
+}
+
+int er_fragopt_slac_accumulate(er_fragopt* dst, er_fragopt* src) {
+  if (!dst || !src || dst == src || dst->JJ.empty() || dst->JJ.size() != src->JJ.size()) { set_err("er_fragopt_slac_accumulate: bad handles"); return ER_ERR_ARG; }
+  for (size_t k = 0; k < dst->JJ.size(); ++k) dst->JJ[k] += src->JJ[k];
   return ER_OK;
 }
 
@@ -338,7 +344,7 @@ int er_fragopt_nonrigid_assemble(er_fragopt* h, double weight) {
       for (int tid = 0; tid < cnt; ++tid) {
         const Corr& c = h->corr[base + tid];
         const StaticPoint &si = h->S[c.gi], &sj = h->S[c.gj];
-        fo_nonrigid_row(si.r, &h->N[3 * c.gi], sj.r, weight, &rows[(size_t)tid * kNrStride]);
+        fo_nonrigid_row(si.r, &h->N[3 * c.gi], sj.r, weight, &rows[(size_t)tid * kNrStride], tid & 7);
         keys[tid].pair = c.pair; keys[tid].bi = si.base; keys[tid].bj = sj.base;
       }
       for (int tid = 0; tid < cnt; ++tid) brk[tid] = !(keys[tid] == (tid == 0 ? cur : keys[tid - 1]));
@@ -348,7 +354,7 @@ int er_fragopt_nonrigid_assemble(er_fragopt* h, double weight) {
           for (int tid = 0; tid < kNrThreads; ++tid) for (int e = 0; e < 16; ++e) acc[tid][e] = 0.0;
           cur = keys[c];
         }
-        for (int tid = 0; tid < kNrTiles; ++tid) fo_tile_mac<kNrStride>(ty[tid], tx[tid], &rows[(size_t)c * kNrStride], acc[tid]);
+        for (int tid = 0; tid < kNrTiles; ++tid) fo_tile_mac<kNrStride>(ty[tid], tx[tid], &rows[(size_t)c * kNrStride], c & 7, acc[tid]);
       }
     }
     if (cur.pair >= 0) flush();

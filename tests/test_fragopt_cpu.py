@@ -278,3 +278,44 @@ def test_bench_loop_on_the_emulated_library_matches_reference_binary(emul, golde
         loop.step()
     assert np.abs(loop.pose - golden["three_slac_pose"]).max() <= POSE_TOL
     assert np.abs(loop.expand().reshape(-1, 3) - golden["three_slac_ctr"]).max() <= CTR_TOL
+
+
+@pytest.mark.parametrize("mode", ["slac", "rigid"])
+def test_emulated_executable_with_three_devices(oracle, emul, golden, tmp_path, mode):
+    """--devices: every "device" holds all fragments and a share of the pairs; the sums are added in device order."""
+    d = str(tmp_path)
+    _, args = helpers.fragopt_case("three", d)
+    p = subprocess.run([emul["exe"]] + args + ["--" + mode, "--devices", "0,1,2", "--bench_json", os.path.join(d, "t.json")], cwd=d,
+                       stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout
+    assert '"devices": 3' in open(os.path.join(d, "t.json")).read()
+    assert np.abs(helpers.read_log_poses(os.path.join(d, "pose.log")) - golden["three_%s_pose" % mode]).max() <= POSE_TOL
+    assert np.abs(np.loadtxt(os.path.join(d, "output.ctr")) - golden["three_%s_ctr" % mode]).max() <= CTR_TOL
+
+
+def accumulate_check(make, tmp_path):
+    """Shared with the GPU tests: two handles with half of the pairs each, accumulated, equal one handle with all pairs."""
+    d, _ = helpers.fragopt_case("three", str(tmp_path))
+    xyzn, pairs, corres, ipose, _ = case_arrays("three", d)
+    num = len(xyzn)
+    rot_t = np.array([ipose[l][:3, :3].T for l in range(num)])
+    hs = [make(num, k) for k in range(3)]
+    shares = [(pairs, corres), (pairs[:1], corres[:1]), (pairs[1:], corres[1:])]
+    out = []
+    for g, (pp, cc) in zip(hs, shares):
+        for l in range(num):
+            g.set_cloud(l, xyzn[l])
+        g.set_pairs(pp, cc)
+        g.update_pose(ipose)
+        out.append(g.slac_assemble(rot_t))
+    full = hs[0].slac_jj()
+    hs[1].slac_accumulate(hs[2])
+    both = hs[1].slac_jj()
+    assert np.abs(both - full).max() <= 1e-11 * np.abs(full).max()
+    assert np.abs(out[1][0] + out[2][0] - out[0][0]).max() <= 1e-11 * np.abs(out[0][0]).max()
+    assert abs(out[1][1] + out[2][1] - out[0][1]) <= 1e-11 * out[0][1]
+
+
+def test_emulated_accumulate(emul, tmp_path):
+    from elasticreconstruction_b200 import capi
+    accumulate_check(lambda num, k: capi.FragOpt(num, 8, 3.0, library=emul["lib"]), tmp_path)

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 import helpers
-from test_fragopt_cpu import api_check, check_executable, nonrigid_api_check
+from test_fragopt_cpu import CTR_TOL, POSE_TOL, accumulate_check, api_check, check_executable, nonrigid_api_check
 
 pytestmark = pytest.mark.gpu
 
@@ -31,6 +31,38 @@ def test_nonrigid_kernels_against_the_oracle(tmp_path):
 @pytest.mark.parametrize("name,mode", helpers.FRAGOPT_CASE_MODES)
 def test_executable_matches_reference_binary(oracle, tmp_path, name, mode):
     check_executable(EXE, oracle, np.load(GOLDEN), str(tmp_path), name, mode)
+
+
+def _device_count():
+    import ctypes
+    try:
+        n = ctypes.c_int(0)
+        rt = ctypes.CDLL("libcudart.so.12")
+        return n.value if rt.cudaGetDeviceCount(ctypes.byref(n)) == 0 else 0
+    except OSError:
+        return 0
+
+
+def test_accumulate_on_one_device(tmp_path):
+    """er_fragopt_slac_accumulate between two handles (here on the same device; across devices in the test below)."""
+    from elasticreconstruction_b200 import capi
+    accumulate_check(lambda num, k: capi.FragOpt(num, 8, 3.0, device=0), tmp_path)
+
+
+@pytest.mark.parametrize("mode", ["slac", "rigid"])
+def test_executable_on_two_devices(tmp_path, mode):
+    if _device_count() < 2:
+        pytest.skip("needs two CUDA devices")
+    from elasticreconstruction_b200 import capi
+    accumulate_check(lambda num, k: capi.FragOpt(num, 8, 3.0, device=k % 2), tmp_path)
+    golden = np.load(GOLDEN)
+    d = str(tmp_path)
+    _, args = helpers.fragopt_case("three", d)
+    p = subprocess.run([EXE] + args + ["--" + mode, "--devices", "0,1"], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
+                       timeout=600)
+    assert p.returncode == 0, p.stdout
+    assert np.abs(helpers.read_log_poses(os.path.join(d, "pose.log")) - golden["three_%s_pose" % mode]).max() <= POSE_TOL
+    assert np.abs(np.loadtxt(os.path.join(d, "output.ctr")) - golden["three_%s_ctr" % mode]).max() <= CTR_TOL
 
 
 def test_sample_file_and_sorted_order_independence(tmp_path):
