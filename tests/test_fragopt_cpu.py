@@ -319,3 +319,84 @@ def accumulate_check(make, tmp_path):
 def test_emulated_accumulate(emul, tmp_path):
     from elasticreconstruction_b200 import capi
     accumulate_check(lambda num, k: capi.FragOpt(num, 8, 3.0, library=emul["lib"]), tmp_path)
+
+
+def _read_sample_pcd(path):
+    """x y z nx ny nz rows of a sample.pcd: `DATA binary` (the reference build's stand-in writer, 32-byte records) or
+    `DATA binary_compressed` (the product: fields one after the other, LZF -- literal runs are all its writer emits)."""
+    raw = open(path, "rb").read()
+    head, _, body = raw.partition(b"DATA ")
+    kind, _, body = body.partition(b"\n")
+    n = int([l for l in head.split(b"\n") if l.startswith(b"POINTS")][0].split()[1])
+    if kind.strip() == b"binary":
+        a = np.frombuffer(body[: 32 * n], dtype="<f4").reshape(n, 8)
+        return a[:, [0, 1, 2, 4, 5, 6]]
+    csize, usize = np.frombuffer(body[:8], dtype="<u4")
+    data, out, p = body[8: 8 + csize], bytearray(), 0
+    while p < len(data):
+        ctrl = data[p]
+        assert ctrl < 32, "back-references are not expected from the product's writer"
+        out += data[p + 1: p + 2 + ctrl]
+        p += 2 + ctrl
+    assert len(out) == usize == 32 * n
+    a = np.frombuffer(bytes(out), dtype="<f4").reshape(8, n).T
+    return a[:, [0, 1, 2, 4, 5, 6]]
+
+
+FRAGOPT_VARIANTS = {
+    # name: (case, mode, extra flags, files to compare besides output.ctr)
+    "slac_sample": ("three", "slac", ["--write_xyzn_sample", "7"], ["sample.pcd"]),
+    "rigid_sample_save_to": ("three", "rigid", ["--write_xyzn_sample", "11", "--save_to", "rigid.ctr"], ["sample.pcd"]),
+    "nonrigid_intermediate_files": ("three_res4", "nonrigid", ["--write_xyzn_sample", "9"],
+                                    ["itr0.ctr", "itr1.ctr", "itr0_inner0_out.ctr", "itr1_inner2_out.ctr", "sample.pcd"]),
+    "slac_init_ctr": ("three", "slac", ["--init_ctr", "INIT_CTR"], []),
+    "nonrigid_ipose": ("three_res4", "nonrigid", ["--ipose", "IPOSE"], []),
+    "slac_resolution5_length": ("three", "slac", ["--resolution", "5", "--length", "3.2", "--weight", "3"], []),
+    "default_mode_is_nonrigid": ("three_res4", "", [], []),
+}
+
+
+@pytest.mark.parametrize("variant", list(FRAGOPT_VARIANTS))
+def test_emulated_executable_flag_variants_against_live_reference(oracle, emul, tmp_path, variant):
+    """Flags beyond the golden cases, the emulated executable against the reference binary run side by side."""
+    if not os.path.exists(oracle.REF_FRAGOPT):
+        pytest.skip("oracle/_ref/FragmentOptimizer_ref not built (needs /root/reference)")
+    case, mode, extra, files = FRAGOPT_VARIANTS[variant]
+    d = str(tmp_path)
+    data, args = helpers.fragopt_case(case, d)
+    c = helpers.FRAGOPT_CASES[case]
+    res = flag(c, "--resolution", 8)
+    if "INIT_CTR" in extra:                                   # a gently bent lattice (nper / 3 rows)
+        r1 = res + 1
+        lat = np.array([[i, j, k] for k in range(r1) for j in range(r1) for i in range(r1)], dtype=np.float64) * (3.0 / res)
+        lat += 0.003 * np.sin(2.0 * lat[:, [2, 0, 1]])
+        np.savetxt(os.path.join(d, "init.ctr"), lat, fmt="%.10f")
+        extra = [os.path.join(d, "init.ctr") if x == "INIT_CTR" else x for x in extra]
+    if "IPOSE" in extra:
+        from elasticreconstruction_b200 import synth
+        poses = [synth.fragment_frame(i) @ synth.perturbation(7000 + i, 0.2, 0.003) for i in range(c["num"])]
+        synth.write_log(os.path.join(d, "ipose.log"), poses)
+        extra = [os.path.join(d, "ipose.log") if x == "IPOSE" else x for x in extra]
+    argv = args + extra + (["--" + mode] if mode else [])
+    ctr_name = extra[extra.index("--save_to") + 1] if "--save_to" in extra else "output.ctr"
+    out = {}
+    for who, run in (("mine", lambda: subprocess.run([emul["exe"]] + argv, cwd=os.path.join(d, "mine"), stdout=subprocess.PIPE,
+                                                     stderr=subprocess.STDOUT, text=True, timeout=900)),
+                     ("ref", lambda: oracle.run_reference_fragopt(argv, cwd=os.path.join(d, "ref")))):
+        os.makedirs(os.path.join(d, who))
+        r = run()
+        if who == "mine":
+            assert r.returncode == 0, r.stdout
+        out[who] = os.path.join(d, who)
+    a, b = np.loadtxt(os.path.join(out["mine"], ctr_name)), np.loadtxt(os.path.join(out["ref"], ctr_name))
+    assert a.shape == b.shape and np.abs(a - b).max() <= CTR_TOL
+    if mode in ("slac", "rigid"):
+        assert np.abs(helpers.read_log_poses(os.path.join(out["mine"], "pose.log")) -
+                      helpers.read_log_poses(os.path.join(out["ref"], "pose.log"))).max() <= POSE_TOL
+    for f in files:
+        if f.endswith(".ctr"):
+            assert np.abs(np.loadtxt(os.path.join(out["mine"], f)) - np.loadtxt(os.path.join(out["ref"], f))).max() <= CTR_TOL, f
+        else:
+            pm, pr = _read_sample_pcd(os.path.join(out["mine"], f)), _read_sample_pcd(os.path.join(out["ref"], f))
+            assert pm.shape == pr.shape and len(pm) > 100
+            assert np.abs(pm[:, :3] - pr[:, :3]).max() <= 1e-6 and np.abs(pm[:, 3:] - pr[:, 3:]).max() <= 1e-5
