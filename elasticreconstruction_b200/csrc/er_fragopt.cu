@@ -27,6 +27,7 @@
 
 #include <algorithm>
 #include <cstdint>
+#include <mutex>
 #include <vector>
 
 #include "er_common.h"
@@ -328,9 +329,8 @@ struct Solver {
 };
 Solver& solver_api() {
   static Solver s;
-  static bool tried = false;
-  if (!tried) {
-    tried = true;
+  static std::once_flag once;
+  std::call_once(once, [] {
     for (const char* name : {"libcusolver.so.11", "libcusolver.so", "/usr/local/cuda/lib64/libcusolver.so.11", "/usr/local/cuda/lib64/libcusolver.so"}) {
       s.dl = dlopen(name, RTLD_NOW | RTLD_LOCAL);
       if (s.dl) break;
@@ -344,7 +344,7 @@ Solver& solver_api() {
       s.potrs = (decltype(s.potrs))dlsym(s.dl, "cusolverDnDpotrs");
       s.ok = s.create && s.destroy && s.set_stream && s.potrf_buffer && s.potrf && s.potrs;
     }
-  }
+  });
   return s;
 }
 }  // namespace
@@ -735,7 +735,7 @@ int er_fragopt_slac_solve(er_fragopt* h, const double* base, const double* rhs, 
     }                                                                                            \
   } while (0)
   Solver& S = solver_api();
-  if (!S.ok) { er::set_error("er_fragopt_slac_solve: cannot load libcusolver (%s)", dlerror() ? dlerror() : "symbols missing"); return ER_ERR_CUDA; }
+  if (!S.ok) { er::set_error("er_fragopt_slac_solve: cannot load libcusolver"); return ER_ERR_CUDA; }
   if (!h->solver) {
     ER_SOLVER(S.create(&h->solver));
     ER_SOLVER(S.set_stream(h->solver, h->stream));
