@@ -224,8 +224,10 @@ struct App {
     return true;
   }
 
-  // PointCloud::LoadFromXYZNFile's parse: a line that does not scan leaves the previous values in place
-  static void read_xyzn(const std::string& fn, std::vector<float>& rows) {
+  // PointCloud::LoadFromXYZNFile's parse (PointCloud.cpp:46-63): sscanf into ONE array that lives across lines, so a line
+  // that does not scan (blank, too few numbers) repeats what the array holds -- and what it holds has been through
+  // GetCoordinate, which divides the normal by unit_length_ IN PLACE (PointCloud.h:136-138) once the point is in bounds.
+  static void read_xyzn(const std::string& fn, std::vector<float>& rows, float unit, int res) {
     FILE* f = fopen(fn.c_str(), "r");
     if (!f) return;
     char buf[1024];
@@ -234,6 +236,9 @@ struct App {
       if (strlen(buf) > 0 && buf[0] != '#') {
         sscanf(buf, "%f %f %f %f %f %f", &x[0], &x[1], &x[2], &x[3], &x[4], &x[5]);
         rows.insert(rows.end(), x, x + 6);
+        const int c0 = (int)floorf(x[0] / unit), c1 = (int)floorf(x[1] / unit), c2 = (int)floorf(x[2] / unit);
+        if (c0 < 0 || c0 >= res || c1 < 0 || c1 >= res || c2 < 0 || c2 >= res) break;     // "Point out of bound": loading stops
+        x[3] /= unit; x[4] /= unit; x[5] /= unit;
       }
     }
     fclose(f);
@@ -258,7 +263,7 @@ struct App {
           }
         state[i] = 1;
       } else if (er_io::file_exists(xyzn)) {
-        read_xyzn(xyzn, rows[i]);
+        read_xyzn(xyzn, rows[i], (float)o.length / o.resolution, o.resolution);
         state[i] = 1;
       } else {
         state[i] = 3;

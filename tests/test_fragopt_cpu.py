@@ -400,3 +400,46 @@ def test_emulated_executable_flag_variants_against_live_reference(oracle, emul, 
             pm, pr = _read_sample_pcd(os.path.join(out["mine"], f)), _read_sample_pcd(os.path.join(out["ref"], f))
             assert pm.shape == pr.shape and len(pm) > 100
             assert np.abs(pm[:, :3] - pr[:, :3]).max() <= 1e-6 and np.abs(pm[:, 3:] - pr[:, 3:]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("mode", ["slac", "rigid"])
+def test_emulated_executable_on_ragged_inputs_against_live_reference(oracle, emul, tmp_path, mode):
+    """Inputs the reference tolerates silently: a rejected pair (frame -1), a pair below --blacklistpair, a pair whose corres file is
+    missing (it still counts as a pair: OptimizeRigid adds its six ones), comment and blank lines in .xyzn and corres files (a
+    line that does not scan repeats the previous point / pair, because sscanf leaves its targets untouched)."""
+    if not os.path.exists(oracle.REF_FRAGOPT):
+        pytest.skip("oracle/_ref/FragmentOptimizer_ref not built (needs /root/reference)")
+    from elasticreconstruction_b200 import synth
+    d = str(tmp_path)
+    data = os.path.join(d, "data") + os.sep
+    ds = synth.make_fragopt_dataset(data, num=4, n_points=4000)
+    # a comment line and a blank line in one cloud and one corres file
+    p = data + "cloud_bin_xyzn_1.xyzn"
+    L = open(p).read().split("\n")
+    L.insert(5, "# a comment")
+    L.insert(9, "")
+    open(p, "w").write("\n".join(L))
+    p = data + "corres_0_1.txt"
+    L = open(p).read().split("\n")
+    L.insert(3, "# comment")
+    L.insert(7, "")
+    open(p, "w").write("\n".join(L))
+    os.remove(data + "corres_1_2.txt")                         # missing file: an accepted pair without correspondences (every
+    #                                                            fragment stays connected: an unconstrained fragment makes the
+    #                                                            system singular -- garbage from the reference, an error from us)
+    recs = []
+    for k, (i, j) in enumerate(ds["pairs"]):
+        n = len(ds["corres"][(i, j)])
+        recs.append((i, j, -1 if (i, j) == (0, 3) else (50 if (i, j) == (2, 3) else n)))    # rejected / below the threshold
+    synth.write_log(data + "reg_output.log", ds["reg_poses"], ids=recs)
+    args = ["--rgbdslam", data + "traj.log", "--registration", data + "reg_output.log", "--dir", data, "--num", "4", "--interval", "1",
+            "--blacklistpair", "1000", "--iteration", "2", "--" + mode]
+    os.makedirs(os.path.join(d, "mine"))
+    os.makedirs(os.path.join(d, "ref"))
+    p = subprocess.run([emul["exe"]] + args, cwd=os.path.join(d, "mine"), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
+    assert p.returncode == 0, p.stdout
+    ref_out = oracle.run_reference_fragopt(args, cwd=os.path.join(d, "ref"))
+    assert p.stdout.count("correspondences.") == ref_out.count("correspondences.") == 4          # four accepted pairs, one of them empty
+    a, b = np.loadtxt(os.path.join(d, "mine", "output.ctr")), np.loadtxt(os.path.join(d, "ref", "output.ctr"))
+    assert np.abs(a - b).max() <= CTR_TOL
+    assert np.abs(helpers.read_log_poses(os.path.join(d, "mine", "pose.log")) - helpers.read_log_poses(os.path.join(d, "ref", "pose.log"))).max() <= POSE_TOL
