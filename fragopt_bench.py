@@ -36,6 +36,16 @@ FMA_PER_ROW = 60 * 61 // 2 + 61          # upper triangle of the 60 x 60 outer p
 FP64_PEAK_TFLOPS = 37.0                  # B200 FP64 (non-tensor) FMA peak, NVIDIA's published figure; not in MEASURED_PEAKS.json
 
 
+def _traffic_per_row():
+    """DRAM bytes per correspondence of slac_assemble_kernel from the committed ncu capture (profiles/traffic.json), or None."""
+    try:
+        import json
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["slac_assemble_kernel"]
+        return float(t["dram_bytes_per_launch"]) / float(t["units_per_launch"])
+    except Exception:
+        return None
+
+
 def lattice_nodes():
     r1 = RES + 1
     unit = LENGTH / RES
@@ -240,7 +250,8 @@ def run(local: int, fragments: int = 50, points: int = 200_000, iterations: int 
         "kernel": {"name": "slac_assemble_kernel", "ms": k_ms, "all_ms": [round(x, 3) for x in kernel_ms], "rows_per_s": rows / (k_ms * 1e-3),
                    "flushes": int(flushes), "rows_per_flush": rows / max(1, flushes)},
         "roofline": {"bound": "fp64 fma", "kernel": "slac_assemble_kernel", "achieved": tflops, "peak": FP64_PEAK_TFLOPS, "unit": "TFLOP/s",
-                     "frac": tflops / FP64_PEAK_TFLOPS, "traffic": None,
+                     "frac": tflops / FP64_PEAK_TFLOPS, "traffic": (_traffic_per_row() * rows) if _traffic_per_row() else None,
+                     "traffic_note": "DRAM bytes of this launch, scaled per correspondence from the committed ncu capture (59 B per row)",
                      "algorithmic_flops_per_row": 2 * FMA_PER_ROW,
                      "note": "1891 double multiply-adds per correspondence against ~100 B of gathers: the kernel's roof is FP64 issue, "
                              "not HBM; the peak is NVIDIA's published FP64 figure for B200 (MEASURED_PEAKS.json has no FP64 entry)"},
