@@ -443,3 +443,36 @@ def test_emulated_executable_on_ragged_inputs_against_live_reference(oracle, emu
     a, b = np.loadtxt(os.path.join(d, "mine", "output.ctr")), np.loadtxt(os.path.join(d, "ref", "output.ctr"))
     assert np.abs(a - b).max() <= CTR_TOL
     assert np.abs(helpers.read_log_poses(os.path.join(d, "mine", "pose.log")) - helpers.read_log_poses(os.path.join(d, "ref", "pose.log"))).max() <= POSE_TOL
+
+
+def test_bench_leg_end_to_end_on_the_emulated_library(emul, monkeypatch):
+    """fragopt_bench.run() (the leg bench.py embeds) with the library replaced by the emulation and the device-side
+    correspondence search by a cKDTree: every line of the leg's Python executes, and its record has the contract's keys."""
+    import importlib.util
+    from scipy.spatial import cKDTree
+    from elasticreconstruction_b200 import capi, synth
+    spec = importlib.util.spec_from_file_location("fragopt_bench", os.path.join(ROOT, "fragopt_bench.py"))
+    fb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fb)
+
+    def corres(frags, pairs, device):
+        out = []
+        for (i, j) in pairs:
+            T = np.linalg.inv(synth.fragment_frame(i)) @ synth.fragment_frame(j)
+            d, idx = cKDTree(frags[i][0].astype(np.float64)).query(frags[j][0].astype(np.float64) @ T[:3, :3].T + T[:3, 3])
+            s = np.nonzero(d < 0.015)[0]
+            out.append(np.stack([idx[s], s], axis=1).astype(np.int32))
+        return out
+
+    real = capi.FragOpt
+    monkeypatch.setattr(fb, "device_correspondences", corres)
+    monkeypatch.setattr(fb.capi, "FragOpt", lambda num, res, length, device=0: real(num, res, length, library=emul["lib"]))
+    r = fb.run(0, fragments=3, points=3000, iterations=2, warmup=1, cpu=os.path.exists(os.path.join(ROOT, "oracle", "_ref", "FragmentOptimizer_ref")))
+    assert r["rows"] > 5000 and r["value"] > 0 and r["e2e"]["value"] > 0 and r["roofline"]["bound"] == "fp64 fma"
+    assert r["roofline"]["traffic"] and abs(r["roofline"]["traffic"] / r["rows"] - 59.45) < 0.1
+    assert r["max_pose_error_vs_truth"] < r["initial_pose_error"]
+    line = fb.as_line(r, None, 1)
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "roofline", "cpu_baseline", "e2e", "gpu_launches"):
+        assert k in line
+    if r["cpu_baseline"]:
+        assert r["cpu_baseline"]["kind"] == "reference" and r["cpu_baseline"]["value"] > 0
