@@ -475,7 +475,7 @@ def main():
             dist.destroy_process_group()
             return 0
         fo = fragopt_bench.run(local, fragments=args.fragopt_fragments, points=args.fragopt_points, iterations=args.fragopt_iterations,
-                               clock_sampler=ClockSampler)
+                               clock_sampler=ClockSampler, peak_gbs=peak)
         sys.stdout.flush()
         os.write(real_stdout, (json.dumps(fragopt_bench.as_line(fo, args, world)) + "\n").encode())
         return 0
@@ -712,7 +712,7 @@ def main():
             import fragopt_bench
             torch.cuda.empty_cache()
             fragopt = fragopt_bench.run(local, fragments=args.fragopt_fragments, points=args.fragopt_points,
-                                        iterations=args.fragopt_iterations, clock_sampler=ClockSampler)
+                                        iterations=args.fragopt_iterations, clock_sampler=ClockSampler, peak_gbs=peak)
         except Exception as e:      # noqa: BLE001
             fragopt = {"error": "%s: %s" % (type(e).__name__, e)}
         torch.cuda.empty_cache()

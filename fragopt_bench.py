@@ -193,8 +193,11 @@ def reference_sample(iterations: int, num: int = 4, points: int = 20000):
     return rows, ms[0] * 1e-3 / iterations, min(8, os.cpu_count() or 1)
 
 
+ALG_BYTES_PER_ROW = 16 + 5 * 16         # the sorted correspondence (int4) + five 16-byte gathers (cell/residuals, position, normal of pi; cell/residuals, position of pj)
+
+
 def run(local: int, fragments: int = 50, points: int = 200_000, iterations: int = 3, warmup: int = 1, cpu: bool = True,
-        clock_sampler=None):
+        clock_sampler=None, peak_gbs: float = 0.0):
     frags = [synth.make_local_fragment(i, points) for i in range(fragments)]
     pairs = [(i, j) for i in range(fragments) for j in range(i + 1, fragments)]
     corres = device_correspondences(frags, pairs, local)
@@ -253,6 +256,9 @@ def run(local: int, fragments: int = 50, points: int = 200_000, iterations: int 
                      "frac": tflops / FP64_PEAK_TFLOPS, "traffic": (_traffic_per_row() * rows) if _traffic_per_row() else None,
                      "traffic_note": "DRAM bytes of this launch, scaled per correspondence from the committed ncu capture (59 B per row)",
                      "algorithmic_flops_per_row": 2 * FMA_PER_ROW,
+                     "hbm_view": {"algorithmic_bytes_per_row": ALG_BYTES_PER_ROW, "achieved": ALG_BYTES_PER_ROW * rows / (k_ms * 1e-3) / 1e9,
+                                  "peak": peak_gbs or None, "unit": "GB/s",
+                                  "frac": (ALG_BYTES_PER_ROW * rows / (k_ms * 1e-3) / 1e9 / peak_gbs) if peak_gbs else None},
                      "note": "1891 double multiply-adds per correspondence against ~100 B of gathers: the kernel's roof is FP64 issue, "
                              "not HBM; the peak is NVIDIA's published FP64 figure for B200 (MEASURED_PEAKS.json has no FP64 entry)"},
         "e2e": {"value": rows * iterations / e2e_s, "unit": "correspondences/s", "h2d_bytes_per_step": int(h2d / iterations),
