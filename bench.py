@@ -410,6 +410,9 @@ def main():
     ap.add_argument("--fusion", type=int, default=32, help="frames per fused launch triple (1..32)")
     ap.add_argument("--no-icp", action="store_true")
     ap.add_argument("--no-fragopt", action="store_true")
+    ap.add_argument("--fragopt-multi", action="store_true",
+                    help="N > 1 only: run the FragmentOptimizer leg sharded over the ranks (pairs round-robin + one all-reduce of the matrix "
+                         "per iteration).  Off by default: gloo-tested on the CPU, not yet run on several GPUs")
     ap.add_argument("--fragopt-fragments", type=int, default=50)
     ap.add_argument("--fragopt-points", type=int, default=200000)
     ap.add_argument("--fragopt-iterations", type=int, default=3)
@@ -715,6 +718,12 @@ def main():
                                         iterations=args.fragopt_iterations, clock_sampler=ClockSampler, peak_gbs=peak)
         except Exception as e:      # noqa: BLE001
             fragopt = {"error": "%s: %s" % (type(e).__name__, e)}
+        torch.cuda.empty_cache()
+    if not args.no_fragopt and world > 1 and args.fragopt_multi:
+        import fragopt_bench
+        torch.cuda.empty_cache()
+        fragopt = fragopt_bench.run_sharded(local, rank, world, fragments=args.fragopt_fragments, points=args.fragopt_points,
+                                            iterations=args.fragopt_iterations)
         torch.cuda.empty_cache()
     cpu = None
     if rank == 0 and world == 1 and args.cpu_frames > 0:

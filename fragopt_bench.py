@@ -361,3 +361,86 @@ def nonrigid_probe(local: int, fragments: int = 8, points: int = 50_000, weight:
                               "fp64_tflops": 2.0 * (48 * 49 // 2) * rows / (ms * 1e-3) / 1e12, "x_finite": bool(np.isfinite(x).all())}
     g.close()
     return out
+
+
+# ------------------------------------------------------------------------------------------------ several ranks (opt-in)
+class ShardedSlacLoop(SlacLoop):
+    """OptimizeSLAC with the pair list dealt over the ranks of a torch.distributed group: every rank holds all fragments and
+    assembles the normal equations of its pairs; ONE all-reduce per iteration sums the matrices (49 MB for 50 fragments), Jb
+    and the score; every rank then solves the same system and applies the same update.  The summed matrix reaches the
+    solver as base + (sum - own): er_fragopt_slac_solve adds the rank's own assembled matrix on the device.
+
+    `reduce(buf)` sums a float64 numpy vector over the ranks in place (NCCL through a device tensor in the bench, gloo in the
+    CPU test).  Written after the round's GPU minutes were spent: exercised on the CPU (gloo, emulated library,
+    tests/test_fragopt_cpu.py::test_sharded_loop_world2), not yet on several GPUs; bench.py runs it only with --fragopt-multi."""
+
+    def __init__(self, g, ipose, reduce, weight=1.0):
+        super().__init__(g, ipose, weight)
+        self.reduce = reduce
+
+    def step(self):
+        rot_t = np.array([self.pose[l][:3, :3].T for l in range(self.num)])
+        Jb, score = self.g.slac_assemble(rot_t)
+        own = self.g.slac_jj()
+        M = self.M
+        buf = np.empty(M * M + M + 1)
+        buf[:M * M] = own.ravel()
+        buf[M * M:M * M + M] = Jb
+        buf[-1] = score
+        self.reduce(buf)
+        total, Jb, score = buf[:M * M].reshape(M, M), buf[M * M:M * M + M].copy(), float(buf[-1])
+        base_jb, reg = regulariser(self.ictr, self.ctr, self.num, self.w, self.nb)
+        x = -self.g.slac_solve(self.base + (total - own), Jb + base_jb)
+        self.ctr[6 * self.num:] += x[6 * self.num:]
+        for l in range(self.num):
+            T = np.eye(4)
+            T[:3, :3] = rot_zyx(x[6 * l: 6 * l + 3])
+            T[:3, 3] = x[6 * l + 3: 6 * l + 6]
+            self.pose[l] = T @ self.pose[l]
+        self.g.update_points_pn(self.expand())
+        self.scores.append((score, reg))
+        return score
+
+
+def run_sharded(local: int, rank: int, world: int, fragments: int = 50, points: int = 200_000, iterations: int = 3, warmup: int = 1):
+    """The leg on `world` ranks (bench.py --fragopt-multi): pairs round-robin, matrix all-reduce over NCCL."""
+    import torch
+    import torch.distributed as dist
+    frags = [synth.make_local_fragment(i, points) for i in range(fragments)]
+    pairs = [(i, j) for i in range(fragments) for j in range(i + 1, fragments)]
+    mine = pairs[rank::world]
+    corres = device_correspondences(frags, mine, local)
+    rows = int(sum(len(c) for c in corres))
+    g = capi.FragOpt(fragments, RES, LENGTH, device=local)
+    for l in range(fragments):
+        g.set_cloud(l, np.concatenate([frags[l][0], frags[l][1]], axis=1))
+    g.set_pairs(mine, corres)
+    dev = torch.device("cuda", local)
+
+    def reduce(buf):
+        t = torch.from_numpy(buf).to(dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        buf[:] = t.cpu().numpy()
+
+    loop = ShardedSlacLoop(g, np.array([synth.fragopt_initial_pose(i) for i in range(fragments)]), reduce)
+    for _ in range(warmup):
+        loop.step()
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(iterations):
+        loop.step()
+    torch.cuda.synchronize()
+    t = torch.tensor([time.perf_counter() - t0, float(rows)], dtype=torch.float64, device=dev)
+    tmax = t.clone()
+    dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    total_rows = float(t[1].item())
+    sec = float(tmax[0].item())
+    ms, _, _ = g.assemble_stats()
+    g.close()
+    return {"metric": METRIC, "value": total_rows * iterations / sec, "unit": "correspondences/s", "ranks": world,
+            "rows": int(total_rows), "rows_this_rank": rows, "iterations": iterations, "ms_per_iteration": sec * 1e3 / iterations,
+            "assemble_kernel_ms_rank0": ms, "exchange_bytes_per_iteration": int((g.M * g.M + g.M + 1) * 8),
+            "sharding": "pairs round-robin over %d ranks, every rank holds all fragments; one all-reduce of the matrix per iteration" % world,
+            "data_error_scores": [round(s[0], 4) for s in loop.scores]}

@@ -476,3 +476,65 @@ def test_bench_leg_end_to_end_on_the_emulated_library(emul, monkeypatch):
         assert k in line
     if r["cpu_baseline"]:
         assert r["cpu_baseline"]["kind"] == "reference" and r["cpu_baseline"]["value"] > 0
+
+
+def _sharded_worker(rank, world, port, libpath, q):
+    import ctypes
+    import importlib.util
+    import sys
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import tempfile
+    import torch
+    import torch.distributed as dist
+    from elasticreconstruction_b200 import capi
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    spec = importlib.util.spec_from_file_location("fragopt_bench", os.path.join(ROOT, "fragopt_bench.py"))
+    fb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fb)
+    with tempfile.TemporaryDirectory() as d:
+        data, _ = helpers.fragopt_case("three", d)
+    xyzn, pairs, corres, ipose, _ = case_arrays("three", data)
+    lib = ctypes.CDLL(libpath)
+    g = capi.FragOpt(len(xyzn), 8, 3.0, library=lib)
+    for l in range(len(xyzn)):
+        g.set_cloud(l, xyzn[l])
+    g.set_pairs(pairs[rank::world], corres[rank::world])
+
+    def reduce(buf):
+        t = torch.from_numpy(buf)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    loop = fb.ShardedSlacLoop(g, ipose, reduce)
+    for _ in range(2):
+        loop.step()
+    dist.barrier()
+    dist.destroy_process_group()
+    q.put((rank, loop.pose, loop.expand().reshape(-1, 3)))
+
+
+def test_sharded_loop_world2(emul, golden):
+    """fragopt_bench.ShardedSlacLoop on two gloo ranks (pairs dealt round-robin, one all-reduce of the matrix per iteration) against
+    the reference binary's result."""
+    import socket
+    import torch.multiprocessing as mp
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    lib = os.path.join(OUT, "libfragopt_emul.so")
+    procs = [ctx.Process(target=_sharded_worker, args=(r, 2, port, lib, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=600) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    for rank, pose, ctr in res:
+        assert np.abs(pose - golden["three_slac_pose"]).max() <= POSE_TOL
+        assert np.abs(ctr - golden["three_slac_ctr"]).max() <= CTR_TOL
