@@ -1,4 +1,4 @@
-"""Executable-level throughput of the two drop-in binaries, files in -> files out (run on the GPU box):
+"""Executable-level throughput of the drop-in binaries, files in -> files out (run on the GPU box):
 
     python tools/bench_apps.py [--frames 1000] [--fragments 50] [--points 200000] [--devices 0[,1,..]] [--out gpurun_out/r2_apps.json]
 
@@ -6,6 +6,7 @@
   BuildCorrespondence  BASELINE configs[2]: cloud_bin_<i>.pcd + pairs.log, `--reg_traj .. --registration --reg_num 0
                        --fixed_iters` -> reg_output.log + corres_<i>_<j>.txt, `--bench_json` timings (PCD load, upload, gate,
                        ICP, correspondence pass, corres file writes)
+  FragmentOptimizer    --slac on the files BuildCorrespondence just wrote (reg_output.log, corres_<i>_<j>.txt) and the fragments' PCD files
 Inputs are generated once into a scratch directory (not timed); the page cache is warm, as it is for the reference
 binary timed the same way.
 """
@@ -91,6 +92,29 @@ def main():
             res["BuildCorrespondence"] = {"workload": "configs[2]: %d fragments ~%dk points (binary PCD), all %d pairs, --registration --reg_num 0 "
                                                       "--fixed_iters, corres files written" % (n, args.points // 1000, len(pairs)), "runs": runs}
             print(json.dumps(res["BuildCorrespondence"]), flush=True)
+            # ---------------- FragmentOptimizer --slac on BuildCorrespondence's own output files (added after the round's GPU
+            # minutes were spent: this block has not run yet)
+            try:
+                cwd = os.path.join(d, "run1")
+                traj = [np.linalg.inv(synth.BASEPOSE) @ synth.fragopt_initial_pose(i) @ synth.BASEPOSE for i in range(n)]
+                synth.write_log(os.path.join(d, "fo_traj.log"), traj)
+                fo = os.path.join(d, "fo")
+                os.makedirs(fo)
+                t0 = time.perf_counter()
+                p = subprocess.run([os.path.join(BIN, "FragmentOptimizer"), "--slac", "--rgbdslam", os.path.join(d, "fo_traj.log"), "--registration",
+                                    os.path.join(cwd, "reg_output.log"), "--dir", d + os.sep, "--num", str(n), "--interval", "1", "--blacklistpair", "1000",
+                                    "--iteration", "5", "--devices", args.devices, "--bench_json", os.path.join(fo, "fo.json")],
+                                   cwd=fo, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True)
+                wall = time.perf_counter() - t0
+                assert p.returncode == 0, p.stderr[-2000:]
+                j = json.load(open(os.path.join(fo, "fo.json")))
+                j["process_wall_ms"] = wall * 1e3
+                j["correspondences_per_s_iterations"] = j["rows_assembled"] / max(1e-9, (j["assemble_ms"] + j["regulariser_ms"] + j["solve_ms"] + j["update_ms"]) * 1e-3)
+                res["FragmentOptimizer"] = {"workload": "--slac, 5 iterations, on the %d fragments' PCD files and the corres files BuildCorrespondence wrote" % n,
+                                            "run": j}
+                print(json.dumps(res["FragmentOptimizer"]), flush=True)
+            except Exception as e:      # noqa: BLE001
+                res["FragmentOptimizer"] = {"error": "%s: %s" % (type(e).__name__, e)}
     os.makedirs(os.path.dirname(args.out), exist_ok=True)
     json.dump(res, open(args.out, "w"), indent=1)
 
