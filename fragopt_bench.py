@@ -33,7 +33,8 @@ RES, LENGTH = 8, 3.0
 METRIC = "correspondences/sec through SLAC iterations (FragmentOptimizer --slac)"
 WORKLOAD = "FragmentOptimizer --slac: %d synthetic fragments ~%dk pts, %d pairs, %d correspondences, %d iterations"
 FMA_PER_ROW = 60 * 61 // 2 + 61          # upper triangle of the 60 x 60 outer product + b * row + b * b
-FP64_PEAK_TFLOPS = 37.0                  # B200 FP64 (non-tensor) FMA peak, NVIDIA's published figure; not in MEASURED_PEAKS.json
+FP64_PEAK_TFLOPS = 37.2                  # 148 SMs x 64 FP64 FMA/clk x 1.965 GHz x 2; ncu agrees (FP64 pipe 24.8 % busy at 0.48 warp-DFMA/clk/SM,
+#                                          profiles/r2_slac_assemble_kernel.txt); MEASURED_PEAKS.json has no FP64 entry
 
 
 def _traffic_per_row():
@@ -260,7 +261,7 @@ def run(local: int, fragments: int = 50, points: int = 200_000, iterations: int 
                                   "peak": peak_gbs or None, "unit": "GB/s",
                                   "frac": (ALG_BYTES_PER_ROW * rows / (k_ms * 1e-3) / 1e9 / peak_gbs) if peak_gbs else None},
                      "note": "1891 double multiply-adds per correspondence against ~100 B of gathers: the kernel's roof is FP64 issue, "
-                             "not HBM; the peak is NVIDIA's published FP64 figure for B200 (MEASURED_PEAKS.json has no FP64 entry)"},
+                             "not HBM; peak = 148 SMs x 64 FMA/clk x 1.965 GHz (MEASURED_PEAKS.json has no FP64 entry; ncu's FP64-pipe utilisation agrees with it)"},
         "e2e": {"value": rows * iterations / e2e_s, "unit": "correspondences/s", "h2d_bytes_per_step": int(h2d / iterations),
                 "d2h_bytes_per_step": int(g.M * 8 * 2),
                 "setup_s": t_setup, "note": "first %d iterations of the process incl. point upload + GetCoordinate, correspondence upload + "
