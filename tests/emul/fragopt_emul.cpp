@@ -7,7 +7,7 @@
 // VERBATIM reference binary's (oracle/_ref/FragmentOptimizer_ref).  Never built into the product.
 //
 // What it cannot cover is the CUDA glue of er_fragopt.cu (launch geometry, cub radix sort, cuSOLVER): that is the
-// business of tests/test_fragopt_gpu.py.
+// business of tests/test_z_fragopt_gpu.py.
 #include <algorithm>
 #include <cstdarg>
 #include <cstdint>

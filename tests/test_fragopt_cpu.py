@@ -89,7 +89,7 @@ def test_numpy_oracle_matches_reference_binary(golden, tmp_path, name, mode):
 
 
 def check_executable(exe, oracle, golden, d, name, mode):
-    """Shared with tests/test_fragopt_gpu.py: run `exe` on a case and compare its files with the reference binary's."""
+    """Shared with tests/test_z_fragopt_gpu.py: run `exe` on a case and compare its files with the reference binary's."""
     _, args = helpers.fragopt_case(name, d)
     p = subprocess.run([exe] + args + ["--" + mode, "--bench_json", os.path.join(d, "t.json")], cwd=d, stdout=subprocess.PIPE,
                        stderr=subprocess.STDOUT, text=True, timeout=900)
@@ -122,7 +122,7 @@ def test_emulated_kernels_against_the_oracle(emul, tmp_path):
 
 
 def api_check(make, tmp_path, vary_emulated_ctas=False):
-    """Shared with tests/test_fragopt_gpu.py: `make(num)` returns a capi.FragOpt on the library under test."""
+    """Shared with tests/test_z_fragopt_gpu.py: `make(num)` returns a capi.FragOpt on the library under test."""
     import fragopt_oracle as fo
     d, _ = helpers.fragopt_case("three", str(tmp_path))
     xyzn, pairs, corres, ipose, _ = case_arrays("three", d)

@@ -4,7 +4,7 @@
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 S=$SECONDS
-timeout 300 python -m pytest tests/test_fragopt_gpu.py -x -q --timeout 280 > gpurun_out/r2_fragopt_gputests.log 2>&1; echo "fragopt pytest rc=$? t=$((SECONDS-S))"; tail -15 gpurun_out/r2_fragopt_gputests.log
+timeout 300 python -m pytest tests/test_z_fragopt_gpu.py -x -q --timeout 280 > gpurun_out/r2_fragopt_gputests.log 2>&1; echo "fragopt pytest rc=$? t=$((SECONDS-S))"; tail -15 gpurun_out/r2_fragopt_gputests.log
 timeout 120 python tools/profile_fragopt.py 8 50000 2 > gpurun_out/r2_fragopt_small.json 2> gpurun_out/r2_fragopt_small.err; echo "small rc=$? t=$((SECONDS-S))"; tail -3 gpurun_out/r2_fragopt_small.err; cut -c1-1500 gpurun_out/r2_fragopt_small.json
 timeout 400 python bench.py --metric fragopt > gpurun_out/r2_bench_fragopt.json 2> gpurun_out/r2_bench_fragopt.err; echo "fragopt bench rc=$? t=$((SECONDS-S))"; tail -3 gpurun_out/r2_bench_fragopt.err; cut -c1-3000 gpurun_out/r2_bench_fragopt.json
 timeout 200 ncu --set full --clock-control none --import-source on -k regex:slac_assemble -s 1 -c 1 -f -o gpurun_out/prof_slac_assemble_r2 python tools/profile_fragopt.py 20 100000 1 > gpurun_out/r2_ncu_slac.log 2>&1; echo "ncu rc=$? t=$((SECONDS-S))"; tail -2 gpurun_out/r2_ncu_slac.log | cut -c1-300

@@ -6,10 +6,10 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 S=$SECONDS
 V=elasticreconstruction_b200/variants
-timeout 300 python -m pytest tests/test_fragopt_gpu.py -x -q --timeout 280 > gpurun_out/r2_fragopt_gputests2.log 2>&1; echo "fragopt pytest rc=$? t=$((SECONDS-S))"; tail -12 gpurun_out/r2_fragopt_gputests2.log
+timeout 300 python -m pytest tests/test_z_fragopt_gpu.py -x -q --timeout 280 > gpurun_out/r2_fragopt_gputests2.log 2>&1; echo "fragopt pytest rc=$? t=$((SECONDS-S))"; tail -12 gpurun_out/r2_fragopt_gputests2.log
 for v in default fo_natural fo_b96 fo_b64; do
   if [ $v = default ]; then unset ER_B200_LIB; else export ER_B200_LIB=$PWD/$V/libelastic_b200_$v.so; fi
-  if [ $v != default ]; then timeout 120 python -m pytest tests/test_fragopt_gpu.py -q -k "kernels_against and not nonrigid" --timeout 100 2>&1 | tail -1; fi
+  if [ $v != default ]; then timeout 120 python -m pytest tests/test_z_fragopt_gpu.py -q -k "kernels_against and not nonrigid" --timeout 100 2>&1 | tail -1; fi
   timeout 120 python tools/profile_fragopt.py 20 100000 1 > gpurun_out/r2_fragopt_ab_$v.json 2> gpurun_out/r2_fragopt_ab_$v.err
   echo "variant $v rc=$? t=$((SECONDS-S)) $(python -c "
 import json,sys

@@ -5,7 +5,7 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 S=$SECONDS
 V=elasticreconstruction_b200/variants
-timeout 100 python -m pytest tests/test_fragopt_gpu.py -x -q --timeout 90 > gpurun_out/r2_fragopt_gputests3.log 2>&1; echo "fragopt pytest rc=$? t=$((SECONDS-S))"; tail -6 gpurun_out/r2_fragopt_gputests3.log
+timeout 100 python -m pytest tests/test_z_fragopt_gpu.py -x -q --timeout 90 > gpurun_out/r2_fragopt_gputests3.log 2>&1; echo "fragopt pytest rc=$? t=$((SECONDS-S))"; tail -6 gpurun_out/r2_fragopt_gputests3.log
 for v in default fo_noswz fo_b128; do
   if [ $v = default ]; then unset ER_B200_LIB; else export ER_B200_LIB=$PWD/$V/libelastic_b200_$v.so; fi
   timeout 60 python tools/profile_fragopt.py 20 100000 1 > gpurun_out/r2_fragopt_ab3_$v.json 2> gpurun_out/r2_fragopt_ab3_$v.err
