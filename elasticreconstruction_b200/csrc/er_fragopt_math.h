@@ -239,8 +239,21 @@ ER_FO_FN void fo_tile_of(int tid, int* ty, int* tx) {
 
 struct alignas(16) D2 { double x, y; };
 
+// ER_FO_JB_DIAG (compile-time option, default off: found after the round's last GPU session, checked on the CPU emulation
+// only -- tests/test_fragopt_cpu.py::test_emulated_kernels_with_the_diagonal_jb_variant).  The eight b * row threads share a
+// warp with 24 tile threads, which therefore runs two paths per row (19.7 % of the kernel's warp instructions,
+// profiles/r2_slac_assemble_lines.txt).  With this option nobody owns b * row: a diagonal tile (ty == tx) needs only the ten
+// products on or above its diagonal, so four of its six idle accumulators -- (1,0), (2,0), (2,1), (3,0) -- sum b * a0..a3
+// (the Jb entries of positions 4t .. 4t+3; its row operands are already in registers) and, for tile (0,0), (3,1) sums b*b.
+// Operand selects instead of a second path.  Arithmetic verified on the emulation; NOT tuned: as compiled today (nvcc 12.9, 128-register
+// cap) the selects push the accumulators into local memory inside the row loop (STL.128 per row in the SASS), so it needs a pass over
+// the register budget before it can be expected to win.
+#ifndef ER_FO_JB_DIAG
+#define ER_FO_JB_DIAG 0
+#endif
+
 // acc[16] += a (x) b for the 4x4 tile (ty, tx) of row^T row
-template <int STRIDE>
+template <int STRIDE, bool JB = false>
 ER_FO_FN void fo_tile_mac(int ty, int tx, const double* row, int sw, double* acc) {
   // four 128-bit shared-memory loads (rows are 16-byte aligned)
 #if ER_FO_PLANES && ER_FO_SWIZZLE
@@ -260,6 +273,18 @@ ER_FO_FN void fo_tile_mac(int ty, int tx, const double* row, int sw, double* acc
   // fused multiply-adds: the order of the sums differs from the reference's anyway (per-pair dense matrices added
   // under an OpenMP critical section, OptApp.cpp:562-569), so only the tolerance matters here, and DFMA is the roof
   acc[0] = fma(a0, b0, acc[0]); acc[1] = fma(a0, b1, acc[1]); acc[2] = fma(a0, b2, acc[2]); acc[3] = fma(a0, b3, acc[3]);
+#if ER_FO_JB_DIAG
+  if (JB) {
+    const bool diag = ty == tx;
+    const double bv = row[fo_spos<STRIDE>(60, sw)];
+    acc[4] = fma(diag ? bv : a1, diag ? a0 : b0, acc[4]); acc[5] = fma(a1, b1, acc[5]); acc[6] = fma(a1, b2, acc[6]); acc[7] = fma(a1, b3, acc[7]);
+    acc[8] = fma(diag ? bv : a2, diag ? a1 : b0, acc[8]); acc[9] = fma(diag ? bv : a2, diag ? a2 : b1, acc[9]);
+    acc[10] = fma(a2, b2, acc[10]); acc[11] = fma(a2, b3, acc[11]);
+    acc[12] = fma(diag ? bv : a3, diag ? a3 : b0, acc[12]); acc[13] = fma(diag ? bv : a3, diag ? bv : b1, acc[13]);
+    acc[14] = fma(a3, b2, acc[14]); acc[15] = fma(a3, b3, acc[15]);
+    return;
+  }
+#endif
   acc[4] = fma(a1, b0, acc[4]); acc[5] = fma(a1, b1, acc[5]); acc[6] = fma(a1, b2, acc[6]); acc[7] = fma(a1, b3, acc[7]);
   acc[8] = fma(a2, b0, acc[8]); acc[9] = fma(a2, b1, acc[9]); acc[10] = fma(a2, b2, acc[10]); acc[11] = fma(a2, b3, acc[11]);
   acc[12] = fma(a3, b0, acc[12]); acc[13] = fma(a3, b1, acc[13]); acc[14] = fma(a3, b2, acc[14]); acc[15] = fma(a3, b3, acc[15]);
@@ -267,6 +292,10 @@ ER_FO_FN void fo_tile_mac(int ty, int tx, const double* row, int sw, double* acc
 
 // one staged row: the tile threads add their tile, the eight vector threads acc[0..7] += b * row[8u..]
 ER_FO_FN void fo_slac_mac(int tid, int ty, int tx, const double* row, int sw, double* acc) {
+#if ER_FO_JB_DIAG
+  if (tid < 120) fo_tile_mac<kRowStride, true>(ty, tx, row, sw, acc);
+  return;
+#endif
   if (tid < 120) {
     fo_tile_mac<kRowStride>(ty, tx, row, sw, acc);
   } else {
@@ -291,7 +320,17 @@ ER_FO_FN void fo_slac_flush(const Lattice& L, int num, int M, int i, int j, cons
     for (int r = 0; r < 4; ++r)
       for (int s = 0; s < 4; ++s) {
         const int p = 4 * ty + r, q = 4 * tx + s;
-        if (p > q) continue;                               // lower half of a diagonal tile
+        if (p > q) {                                       // lower half of a diagonal tile
+#if ER_FO_JB_DIAG
+          const double w = acc[4 * r + s];                 // (1,0) (2,0) (2,1) (3,0): b * a0..a3; (3,1) of tile (0,0): b * b
+          if (w != 0.0) {
+            const int e = r == 1 ? 0 : r == 2 ? 1 + s : (s == 0 ? 3 : (s == 1 ? 4 : 5));
+            if (e < 4) ADD(&Jb[gp[e]], w);
+            else if (e == 4 && ty == 0) ADD(score, w);
+          }
+#endif
+          continue;
+        }
         const double v = acc[4 * r + s];
         if (v == 0.0) continue;
         const int a = gp[r], b = gq[s];
@@ -300,7 +339,7 @@ ER_FO_FN void fo_slac_flush(const Lattice& L, int num, int M, int i, int j, cons
         else if (a < b) ADD(&JJ[(size_t)a * M + b], v);
         else ADD(&JJ[(size_t)b * M + a], v);
       }
-  } else {
+  } else if (!ER_FO_JB_DIAG) {
     const int u = tid - 120;
     for (int e = 0; e < 8; ++e) {
       const int q = 8 * u + e;

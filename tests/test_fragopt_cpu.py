@@ -538,3 +538,32 @@ def test_sharded_loop_world2(emul, golden):
     for rank, pose, ctr in res:
         assert np.abs(pose - golden["three_slac_pose"]).max() <= POSE_TOL
         assert np.abs(ctr - golden["three_slac_ctr"]).max() <= CTR_TOL
+
+
+def test_emulated_kernels_with_the_diagonal_jb_variant(tmp_path, golden):
+    """-DER_FO_JB_DIAG=1 (compile-time option of csrc/er_fragopt_math.h, default off, not yet measured on a GPU): the diagonal tiles'
+    idle accumulators sum b * row instead of eight extra threads.  Same API check and the same end result as the default."""
+    import importlib.util
+    from elasticreconstruction_b200 import capi
+    os.makedirs(OUT, exist_ok=True)
+    lib = os.path.join(OUT, "libfragopt_emul_jbdiag.so")
+    srcs = [os.path.join(ROOT, "tests", "emul", "fragopt_emul.cpp"), os.path.join(CSRC, "er_host_math.cpp")]
+    if _stale(lib, srcs + [os.path.join(CSRC, "er_fragopt_math.h")]):
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-fopenmp", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-DER_FO_JB_DIAG=1",
+                               "-I", os.path.join(ROOT, "include"), "-I", CSRC, "-I", "/usr/local/cuda/include"] + srcs + ["-o", lib])
+    L = C.CDLL(lib)
+    api_check(lambda num: capi.FragOpt(num, 8, 3.0, library=L), tmp_path, vary_emulated_ctas=True)
+    spec = importlib.util.spec_from_file_location("fragopt_bench", os.path.join(ROOT, "fragopt_bench.py"))
+    fb = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fb)
+    d, _ = helpers.fragopt_case("three", str(tmp_path / "again"))
+    xyzn, pairs, corres, ipose, _ = case_arrays("three", d)
+    g = capi.FragOpt(len(xyzn), 8, 3.0, library=L)
+    for l in range(len(xyzn)):
+        g.set_cloud(l, xyzn[l])
+    g.set_pairs(pairs, corres)
+    loop = fb.SlacLoop(g, ipose)
+    for _ in range(2):
+        loop.step()
+    assert np.abs(loop.pose - golden["three_slac_pose"]).max() <= POSE_TOL
+    assert np.abs(loop.expand().reshape(-1, 3) - golden["three_slac_ctr"]).max() <= CTR_TOL
